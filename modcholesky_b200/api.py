@@ -1,0 +1,281 @@
+"""Host-side mirror of the reference crate's public API for the hot path.
+
+Reference (argmin-rs/modcholesky v0.2.0)            here
+---------------------------------------------------------------------------------------------
+struct Decomposition<L,E,P>{l,e,p}  lib.rs:109-119    Decomposition(l, e, p)
+trait ModCholeskyGMW81              gmw81.rs:24-32    ModCholeskyGMW81 (mixin; default raises)
+trait ModCholeskySE90               se90.rs:24-32     ModCholeskySE90
+trait ModCholeskySE99               se99.rs:21-29     ModCholeskySE99
+trait GershgorinCircles             gershgorin.rs:15  GershgorinCircles
+impl ... for ndarray::Array2<f64>   gmw81.rs:34-41..  Array2 (numpy-backed), plus the new
+                                                      batched Array3 entry point.
+
+Every method goes through the C-ABI (include/modchol_b200.h) into the sm_100a kernels.
+numpy arrays are passed as HOST buffers (the library stages them through the GPU); torch CUDA
+tensors are passed as DEVICE buffers on torch's current stream (no copies, asynchronous).
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Any, List, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class Decomposition:
+    """lib.rs:109-119: `l` lower triangular (strict upper explicitly zero), `e` the diagonal
+    of E in ORIGINAL index order, `p[i]` the original index at permuted position i, such that
+    P (A + diag(e)) P^T = L L^T with P[i, p[i]] = 1.  Carries `phase2_start` (index at which
+    SE90/SE99 left phase 1, -1 if never) as an extra diagnostic."""
+    l: Any
+    e: Any
+    p: Any
+    phase2_start: Any = None
+
+    @staticmethod
+    def new(l, e, p):  # lib.rs:115-118
+        return Decomposition(l, e, p)
+
+
+class NotSquareError(AssertionError, ValueError):
+    """The reference asserts `self.is_square()` (se90.rs:41, se99.rs:38, gmw81.rs:43)."""
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _factor_numpy(algo: int, mode: int, a: np.ndarray, ngpus: int = 0) -> Decomposition:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b, n = a.shape[0], a.shape[1]
+    l = np.empty_like(a)
+    e = np.empty((b, n), dtype=np.float64)
+    p = np.empty((b, n), dtype=np.uint64)
+    k = np.empty((b,), dtype=np.int32)
+    L = _lib.lib()
+    if ngpus and ngpus != 1:
+        rc = L.modchol_factor_batched_multi_gpu_f64(
+            algo, mode, b, n, a.ctypes.data, l.ctypes.data, e.ctypes.data, p.ctypes.data,
+            k.ctypes.data, int(ngpus) if ngpus > 0 else 0)
+    else:
+        rc = L.modchol_factor_batched_f64(
+            algo, mode, b, n, a.ctypes.data, l.ctypes.data, e.ctypes.data, p.ctypes.data,
+            k.ctypes.data, _lib.MEM_HOST, None)
+    _lib.check(rc)
+    return Decomposition(l, e, p, k)
+
+
+def _factor_torch(algo: int, mode: int, a) -> Decomposition:
+    import torch
+    if not a.is_cuda:
+        raise ValueError("torch tensors must live on a CUDA device (pass numpy for host data); "
+                         "modcholesky_b200 has no CPU path")
+    if a.dtype != torch.float64:
+        raise TypeError("expected float64")
+    a = a.contiguous()
+    b, n = a.shape[0], a.shape[1]
+    with torch.cuda.device(a.device):
+        l = torch.empty_like(a)
+        e = torch.empty((b, n), dtype=torch.float64, device=a.device)
+        p = torch.empty((b, n), dtype=torch.int64, device=a.device)  # same bits as u64 (< 2^63)
+        k = torch.empty((b,), dtype=torch.int32, device=a.device)
+        st = torch.cuda.current_stream(a.device).cuda_stream
+        rc = _lib.lib().modchol_factor_batched_f64(
+            algo, mode, b, n, a.data_ptr(), l.data_ptr(), e.data_ptr(), p.data_ptr(), k.data_ptr(),
+            _lib.MEM_DEVICE, ctypes.c_void_p(st))
+    _lib.check(rc)
+    return Decomposition(l, e, p, k)
+
+
+def factor_batched(algo, a, mode="strict", ngpus: int = 0) -> Decomposition:
+    """`a`: (batch, n, n) float64, numpy (host) or torch CUDA tensor (device).  Returns a
+    Decomposition of (batch,n,n), (batch,n), (batch,n) arrays of the same kind."""
+    if a.ndim != 3 or a.shape[1] != a.shape[2]:
+        raise NotSquareError(f"expected (batch, n, n), got {tuple(a.shape)}")
+    if a.shape[1] < 1:
+        raise NotSquareError("n must be >= 1 (the reference panics for n == 0, se99.rs:190)")
+    ai, mi = _lib.algo_id(algo), _lib.mode_id(mode)
+    if _is_torch(a):
+        return _factor_torch(ai, mi, a)
+    return _factor_numpy(ai, mi, np.asarray(a), ngpus)
+
+
+def factor(algo, a, mode="strict") -> Decomposition:
+    """One (n, n) matrix: the batch = 1 case of the same kernels."""
+    if a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise NotSquareError(f"matrix must be square, got {tuple(a.shape)}")
+    d = factor_batched(algo, a[None], mode)
+    return Decomposition(d.l[0], d.e[0], d.p[0], d.phase2_start[0])
+
+
+# ---- the reference's free-function spelling ---------------------------------------------
+def mod_cholesky_gmw81(a, mode="strict") -> Decomposition:
+    """gmw81.rs:39 -- Gill, Murray & Wright (1981) on one (n,n) or a (batch,n,n) array."""
+    return factor("gmw81", a, mode) if a.ndim == 2 else factor_batched("gmw81", a, mode)
+
+
+def mod_cholesky_se90(a, mode="strict") -> Decomposition:
+    """se90.rs:38 -- Schnabel & Eskow (1990)."""
+    return factor("se90", a, mode) if a.ndim == 2 else factor_batched("se90", a, mode)
+
+
+def mod_cholesky_se99(a, mode="strict") -> Decomposition:
+    """se99.rs:35 -- Schnabel & Eskow (1999)."""
+    return factor("se99", a, mode) if a.ndim == 2 else factor_batched("se99", a, mode)
+
+
+def gershgorin_circles_batched(a):
+    """gershgorin.rs:20-41 for a (batch, n, n) array -> (batch, n, 2) [centre, radius]."""
+    if a.ndim != 3 or a.shape[1] != a.shape[2]:
+        raise NotSquareError(f"expected (batch, n, n), got {tuple(a.shape)}")
+    L = _lib.lib()
+    b, n = a.shape[0], a.shape[1]
+    if _is_torch(a):
+        import torch
+        a = a.contiguous()
+        with torch.cuda.device(a.device):
+            out = torch.empty((b, n, 2), dtype=torch.float64, device=a.device)
+            st = torch.cuda.current_stream(a.device).cuda_stream
+            rc = L.modchol_gershgorin_circles_batched_f64(b, n, a.data_ptr(), out.data_ptr(),
+                                                          _lib.MEM_DEVICE, ctypes.c_void_p(st))
+        _lib.check(rc)
+        return out
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    out = np.empty((b, n, 2), dtype=np.float64)
+    _lib.check(L.modchol_gershgorin_circles_batched_f64(b, n, a.ctypes.data, out.ctypes.data,
+                                                        _lib.MEM_HOST, None))
+    return out
+
+
+def verify_batched(a, d: Decomposition):
+    """The identity every reference test asserts (se99.rs:221-231), on the GPU, for a whole
+    batch: returns (resid, flags); see modchol_verify_batched_f64 in the header."""
+    L = _lib.lib()
+    b, n = a.shape[0], a.shape[1]
+    if _is_torch(a):
+        import torch
+        with torch.cuda.device(a.device):
+            resid = torch.empty((b,), dtype=torch.float64, device=a.device)
+            flags = torch.empty((b,), dtype=torch.int32, device=a.device)
+            st = torch.cuda.current_stream(a.device).cuda_stream
+            rc = L.modchol_verify_batched_f64(
+                b, n, a.contiguous().data_ptr(), d.l.contiguous().data_ptr(),
+                d.e.contiguous().data_ptr(), d.p.contiguous().data_ptr(), resid.data_ptr(),
+                flags.data_ptr(), _lib.MEM_DEVICE, ctypes.c_void_p(st))
+        _lib.check(rc)
+        return resid, flags
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    l = np.ascontiguousarray(d.l, dtype=np.float64)
+    e = np.ascontiguousarray(d.e, dtype=np.float64)
+    p = np.ascontiguousarray(d.p, dtype=np.uint64)
+    resid = np.empty((b,), dtype=np.float64)
+    flags = np.empty((b,), dtype=np.int32)
+    _lib.check(L.modchol_verify_batched_f64(b, n, a.ctypes.data, l.ctypes.data, e.ctypes.data,
+                                            p.ctypes.data, resid.ctypes.data, flags.ctypes.data,
+                                            _lib.MEM_HOST, None))
+    return resid, flags
+
+
+# ---- the reference's trait spelling -----------------------------------------------------
+class ModCholeskyGMW81:
+    """gmw81.rs:24-32: the default body panics with "Not implemented!"."""
+
+    def mod_cholesky_gmw81(self) -> Decomposition:
+        raise NotImplementedError("Not implemented!")
+
+
+class ModCholeskySE90:
+    """se90.rs:24-32."""
+
+    def mod_cholesky_se90(self) -> Decomposition:
+        raise NotImplementedError("Not implemented!")
+
+
+class ModCholeskySE99:
+    """se99.rs:21-29."""
+
+    def mod_cholesky_se99(self) -> Decomposition:
+        raise NotImplementedError("Not implemented!")
+
+
+class GershgorinCircles:
+    """gershgorin.rs:15-18."""
+
+    def gershgorin_circles(self) -> List[Tuple[float, float]]:
+        raise NotImplementedError("Not implemented!")
+
+
+class _ArrayBase:
+    mode = "strict"
+
+    def __init__(self, data, mode: str | None = None):
+        self.data = data if _is_torch(data) else np.asarray(data, dtype=np.float64)
+        if mode is not None:
+            self.mode = mode
+
+    def is_square(self) -> bool:
+        return self.data.shape[-1] == self.data.shape[-2]
+
+
+class Array2(_ArrayBase, ModCholeskyGMW81, ModCholeskySE90, ModCholeskySE99, GershgorinCircles):
+    """Stand-in for `ndarray::Array2<f64>` carrying the reference's trait impls
+    (gmw81.rs:34-41, se90.rs:34-40, se99.rs:31-37, gershgorin.rs:20)."""
+
+    def __init__(self, data, mode=None):
+        super().__init__(data, mode)
+        if self.data.ndim != 2:
+            raise ValueError("Array2 needs a 2-D array")
+
+    def _go(self, algo):
+        if not self.is_square():
+            raise NotSquareError("assertion failed: self.is_square()")
+        return factor(algo, self.data, self.mode)
+
+    def mod_cholesky_gmw81(self) -> Decomposition:
+        return self._go("gmw81")
+
+    def mod_cholesky_se90(self) -> Decomposition:
+        return self._go("se90")
+
+    def mod_cholesky_se99(self) -> Decomposition:
+        return self._go("se99")
+
+    def gershgorin_circles(self):
+        if not self.is_square():
+            raise NotSquareError("assertion failed: self.is_square()")
+        out = gershgorin_circles_batched(self.data[None])[0]
+        if _is_torch(out):
+            out = out.cpu().numpy()
+        return [(float(c), float(r)) for c, r in out]
+
+
+class Array3(_ArrayBase):
+    """The new batched entry point: `Array3<f64>` of shape (batch, n, n) ->
+    Decomposition<Array3<f64>, Array2<f64>, Array2<usize>>."""
+
+    def __init__(self, data, mode=None):
+        super().__init__(data, mode)
+        if self.data.ndim != 3:
+            raise ValueError("Array3 needs a 3-D array")
+
+    def _go(self, algo, ngpus=0):
+        if not self.is_square():
+            raise NotSquareError("assertion failed: self.is_square()")
+        return factor_batched(algo, self.data, self.mode, ngpus)
+
+    def mod_cholesky_gmw81_batched(self, ngpus=0) -> Decomposition:
+        return self._go("gmw81", ngpus)
+
+    def mod_cholesky_se90_batched(self, ngpus=0) -> Decomposition:
+        return self._go("se90", ngpus)
+
+    def mod_cholesky_se99_batched(self, ngpus=0) -> Decomposition:
+        return self._go("se99", ngpus)
+
+    def gershgorin_circles_batched(self):
+        return gershgorin_circles_batched(self.data)

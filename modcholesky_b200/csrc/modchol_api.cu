@@ -1,0 +1,479 @@
+// modchol_api.cu -- the C-ABI of include/modchol_b200.h: argument checking, size-class
+// dispatch, the overlapped host-staging pipeline and the multi-GPU batch split.
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute
+// entry point fails with MODCHOL_ERR_NO_DEVICE.
+#include "../../include/modchol_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "cta_kernels.cuh"
+#include "warp_kernels.cuh"
+
+namespace {
+
+using namespace modchol;
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(MODCHOL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                    \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                         \
+    } while (0)
+
+// ---- per-device cache ------------------------------------------------------------------
+constexpr int kSlots = 3;
+struct Slot {
+    cudaStream_t stream = nullptr;
+    double *a = nullptr, *l = nullptr, *e = nullptr;
+    unsigned long long* p = nullptr;
+    int* k = nullptr;
+    size_t cap_a = 0, cap_v = 0, cap_k = 0;  // capacities in elements: a/l, e/p, k
+};
+struct DeviceCtx {
+    std::mutex mu;  // serialises host-pointer calls on this device
+    bool init = false;
+    int sms = 0;
+    int smem_optin = 0;
+    Slot slots[kSlots];
+};
+constexpr int kMaxDevices = 64;
+DeviceCtx g_ctx[kMaxDevices];
+
+int device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ctx_init(int dev)
+{
+    DeviceCtx& c = g_ctx[dev];
+    if (c.init)
+        return MODCHOL_OK;
+    CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    c.init = true;
+    return MODCHOL_OK;
+}
+
+void slot_free(Slot& s)
+{
+    if (s.a) cudaFree(s.a);
+    if (s.l) cudaFree(s.l);
+    if (s.e) cudaFree(s.e);
+    if (s.p) cudaFree(s.p);
+    if (s.k) cudaFree(s.k);
+    s.a = s.l = s.e = nullptr;
+    s.p = nullptr;
+    s.k = nullptr;
+    s.cap_a = s.cap_v = s.cap_k = 0;
+}
+
+int slot_reserve(Slot& s, size_t mats, int n)
+{
+    if (!s.stream)
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    const size_t need_a = mats * (size_t)n * n, need_v = mats * (size_t)n, need_k = mats;
+    if (s.a && need_a <= s.cap_a && need_v <= s.cap_v && need_k <= s.cap_k)
+        return MODCHOL_OK;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    const size_t ca = std::max(need_a, s.cap_a), cv = std::max(need_v, s.cap_v),
+                 ck = std::max(need_k, s.cap_k);
+    slot_free(s);
+    CUDA_TRY(cudaMalloc(&s.a, ca * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s.l, ca * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s.e, cv * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s.p, cv * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&s.k, ck * sizeof(int)));
+    s.cap_a = ca;
+    s.cap_v = cv;
+    s.cap_k = ck;
+    return MODCHOL_OK;
+}
+
+// ---- size-class dispatch ---------------------------------------------------------------
+enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2 };
+
+int cta_ld(int n) { return (n & 1) ? n : n + 1; }
+
+KernelClass classify(int algo, int mode, int n, int smem_optin)
+{
+    if (warp_kernel_available(algo, mode, n))
+        return kClsWarp;
+    if (smem_optin <= 0)
+        smem_optin = 227 * 1024;
+    if (cta_shared_bytes(n, cta_ld(n), true) <= (size_t)smem_optin)
+        return kClsCtaSmem;
+    return kClsCtaGmem;
+}
+
+template <int T>
+int launch_cta(int algo, int n, long long batch, const double* a, double* l, double* e,
+               unsigned long long* p, int* k, bool use_smem, int sms, cudaStream_t st)
+{
+    const int ld = use_smem ? cta_ld(n) : n;
+    const size_t smem = cta_shared_bytes(n, ld, use_smem);
+    int occ = 1;
+    if (algo == MODCHOL_GMW81) {
+        auto kern = gmw81_cta_kernel<T>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+        const long long grid = std::max(1LL, std::min(batch, (long long)sms * std::max(occ, 1)));
+        kern<<<(unsigned)grid, T, smem, st>>>(n, ld, use_smem ? 1 : 0, batch, a, l, e, p, k);
+    } else {
+        auto kern = se_cta_kernel<T>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+        const long long grid = std::max(1LL, std::min(batch, (long long)sms * std::max(occ, 1)));
+        kern<<<(unsigned)grid, T, smem, st>>>(algo, n, ld, use_smem ? 1 : 0, batch, a, l, e, p, k);
+    }
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return MODCHOL_OK;
+}
+
+// all pointers are device pointers on the current device
+int factor_device(int dev, int algo, int mode, long long batch, int n, const double* a, double* l,
+                  double* e, unsigned long long* p, int* k, cudaStream_t st)
+{
+    if (batch == 0)
+        return MODCHOL_OK;
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    const DeviceCtx& c = g_ctx[dev];
+    const KernelClass cls = classify(algo, mode, n, c.smem_optin);
+    if (cls == kClsWarp) {
+        cudaError_t ce = launch_warp_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "warp kernel launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    const bool use_smem = cls == kClsCtaSmem;
+    if (n <= 128)
+        return launch_cta<128>(algo, n, batch, a, l, e, p, k, use_smem, c.sms, st);
+    if (n <= 512)
+        return launch_cta<256>(algo, n, batch, a, l, e, p, k, use_smem, c.sms, st);
+    return launch_cta<512>(algo, n, batch, a, l, e, p, k, use_smem, c.sms, st);
+}
+
+// host pointers: stage the batch through the device in chunks on kSlots streams so that
+// H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1 overlap.
+int factor_host_on_device(int dev, int algo, int mode, long long batch, int n, const double* a,
+                          double* l, double* e, unsigned long long* p, int* k)
+{
+    CUDA_TRY(cudaSetDevice(dev));
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    if (batch == 0)
+        return MODCHOL_OK;
+    DeviceCtx& c = g_ctx[dev];
+    std::lock_guard<std::mutex> lock(c.mu);
+
+    const size_t nn = (size_t)n * n;
+    const size_t target_bytes = (size_t)96 << 20;  // per-slot input staging size
+    long long chunk = (long long)std::max<size_t>(1, target_bytes / (nn * sizeof(double)));
+    chunk = std::min(chunk, (batch + kSlots - 1) / kSlots);
+    chunk = std::max<long long>(chunk, 1);
+    const int nslots = (int)std::min<long long>(kSlots, (batch + chunk - 1) / chunk);
+    for (int s = 0; s < nslots; ++s) {
+        rc = slot_reserve(c.slots[s], (size_t)chunk, n);
+        if (rc)
+            return rc;
+    }
+    long long off = 0;
+    int ci = 0;
+    while (off < batch) {
+        const long long cnt = std::min(chunk, batch - off);
+        Slot& s = c.slots[ci % nslots];
+        CUDA_TRY(cudaMemcpyAsync(s.a, a + (size_t)off * nn, (size_t)cnt * nn * sizeof(double),
+                                 cudaMemcpyHostToDevice, s.stream));
+        rc = factor_device(dev, algo, mode, cnt, n, s.a, s.l, s.e, s.p, k ? s.k : nullptr, s.stream);
+        if (rc)
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(l + (size_t)off * nn, s.l, (size_t)cnt * nn * sizeof(double),
+                                 cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(e + (size_t)off * n, s.e, (size_t)cnt * n * sizeof(double),
+                                 cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(p + (size_t)off * n, s.p, (size_t)cnt * n * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, s.stream));
+        if (k)
+            CUDA_TRY(cudaMemcpyAsync(k + off, s.k, (size_t)cnt * sizeof(int),
+                                     cudaMemcpyDeviceToHost, s.stream));
+        off += cnt;
+        ++ci;
+    }
+    for (int s = 0; s < nslots; ++s)
+        CUDA_TRY(cudaStreamSynchronize(c.slots[s].stream));
+    return MODCHOL_OK;
+}
+
+int check_common(int algo, int mode, long long batch, int n, const void* a, const void* l,
+                 const void* e, const void* p)
+{
+    if (algo < MODCHOL_GMW81 || algo > MODCHOL_SE99)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown algorithm %d", algo);
+    if (mode != MODCHOL_MODE_STRICT && mode != MODCHOL_MODE_FAST)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown mode %d", mode);
+    if (batch < 0)
+        return fail(MODCHOL_ERR_BAD_ARG, "negative batch %lld", batch);
+    if (n < 1)  // the reference panics for n == 0 (`0..(n-1)` underflow, se99.rs:190)
+        return fail(MODCHOL_ERR_BAD_ARG, "n must be >= 1 (got %d)", n);
+    if (n > MODCHOL_MAX_N)
+        return fail(MODCHOL_ERR_UNSUPPORTED, "n = %d exceeds MODCHOL_MAX_N = %d", n, MODCHOL_MAX_N);
+    if (batch > 0 && (!a || !l || !e || !p))
+        return fail(MODCHOL_ERR_BAD_ARG, "null buffer");
+    return MODCHOL_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int modchol_version(void) { return MODCHOL_VERSION; }
+
+const char* modchol_last_error(void) { return g_err.c_str(); }
+
+int modchol_device_count(void) { return device_count(); }
+
+int64_t modchol_launch_count(void) { return g_launches.load(); }
+
+const char* modchol_kernel_class(int algo, int mode, int32_t n)
+{
+    if (n < 1 || n > MODCHOL_MAX_N || algo < 0 || algo > 2)
+        return "unsupported";
+    switch (classify(algo, mode, n, 0)) {
+    case kClsWarp: return "warp32";
+    case kClsCtaSmem: return "cta_smem";
+    default: return "cta_gmem";
+    }
+}
+
+void modchol_shutdown(void)
+{
+    const int nd = std::min(device_count(), kMaxDevices);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < nd; ++d) {
+        DeviceCtx& c = g_ctx[d];
+        std::lock_guard<std::mutex> lock(c.mu);
+        bool any = false;
+        for (auto& s : c.slots)
+            any = any || s.stream || s.a;
+        if (!any)
+            continue;
+        cudaSetDevice(d);
+        for (auto& s : c.slots) {
+            if (s.stream) {
+                cudaStreamSynchronize(s.stream);
+                slot_free(s);
+                cudaStreamDestroy(s.stream);
+                s.stream = nullptr;
+            }
+        }
+    }
+    cudaSetDevice(cur);
+}
+
+int modchol_factor_batched_f64(int algo, int mode, int64_t batch, int32_t n, const double* a,
+                               double* l, double* e, uint64_t* p, int32_t* phase2_start,
+                               int mem_kind, void* stream)
+{
+    g_err.clear();
+    int rc = check_common(algo, mode, batch, n, a, l, e, p);
+    if (rc)
+        return rc;
+    if (mem_kind != MODCHOL_MEM_HOST && mem_kind != MODCHOL_MEM_DEVICE)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown mem_kind %d", mem_kind);
+    if (device_count() < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= kMaxDevices)
+        return fail(MODCHOL_ERR_UNSUPPORTED, "device index %d too large", dev);
+    if (mem_kind == MODCHOL_MEM_DEVICE)
+        return factor_device(dev, algo, mode, batch, n, a, l, e,
+                             reinterpret_cast<unsigned long long*>(p), phase2_start,
+                             static_cast<cudaStream_t>(stream));
+    return factor_host_on_device(dev, algo, mode, batch, n, a, l, e,
+                                 reinterpret_cast<unsigned long long*>(p), phase2_start);
+}
+
+int modchol_factor_batched_multi_gpu_f64(int algo, int mode, int64_t batch, int32_t n,
+                                         const double* a, double* l, double* e, uint64_t* p,
+                                         int32_t* phase2_start, int ngpus)
+{
+    g_err.clear();
+    int rc = check_common(algo, mode, batch, n, a, l, e, p);
+    if (rc)
+        return rc;
+    const int nd = std::min(device_count(), kMaxDevices);
+    if (nd < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (ngpus <= 0)
+        ngpus = nd;
+    if (ngpus > nd)
+        return fail(MODCHOL_ERR_BAD_ARG, "ngpus = %d but only %d devices are visible", ngpus, nd);
+    int cur = 0;
+    CUDA_TRY(cudaGetDevice(&cur));
+    // contiguous slices: device g gets [g*per, min(batch, (g+1)*per))
+    const long long per = (batch + ngpus - 1) / ngpus;
+    std::vector<int> rcs(ngpus, MODCHOL_OK);
+    std::vector<std::string> errs(ngpus);
+    std::vector<std::thread> th;
+    const size_t nn = (size_t)n * n;
+    for (int g = 0; g < ngpus; ++g) {
+        const long long lo = std::min<long long>(batch, (long long)g * per);
+        const long long hi = std::min<long long>(batch, lo + per);
+        if (hi <= lo)
+            continue;
+        th.emplace_back([=, &rcs, &errs]() {
+            rcs[g] = factor_host_on_device(
+                g, algo, mode, hi - lo, n, a + (size_t)lo * nn, l + (size_t)lo * nn,
+                e + (size_t)lo * n, reinterpret_cast<unsigned long long*>(p) + (size_t)lo * n,
+                phase2_start ? phase2_start + lo : nullptr);
+            if (rcs[g])
+                errs[g] = g_err;  // thread-local of the worker
+        });
+    }
+    for (auto& t : th)
+        t.join();
+    cudaSetDevice(cur);
+    for (int g = 0; g < ngpus; ++g)
+        if (rcs[g])
+            return fail(rcs[g], "device %d: %s", g, errs[g].c_str());
+    return MODCHOL_OK;
+}
+
+int modchol_gershgorin_circles_batched_f64(int64_t batch, int32_t n, const double* a,
+                                           double* circles, int mem_kind, void* stream)
+{
+    g_err.clear();
+    if (batch < 0 || n < 1 || (batch > 0 && (!a || !circles)))
+        return fail(MODCHOL_ERR_BAD_ARG, "bad argument");
+    if (n > MODCHOL_MAX_N)
+        return fail(MODCHOL_ERR_UNSUPPORTED, "n too large");
+    if (device_count() < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (batch == 0)
+        return MODCHOL_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    const size_t nn = (size_t)n * n;
+    const long long total = batch * (long long)n;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)g_ctx[dev].sms * 16);
+    if (mem_kind == MODCHOL_MEM_DEVICE) {
+        gershgorin_circles_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(batch, n, a, circles);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+        return MODCHOL_OK;
+    }
+    if (mem_kind != MODCHOL_MEM_HOST)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown mem_kind %d", mem_kind);
+    double *da = nullptr, *dc = nullptr;
+    CUDA_TRY(cudaMalloc(&da, batch * nn * sizeof(double)));
+    cudaError_t ce = cudaMalloc(&dc, (size_t)total * 2 * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemcpy(da, a, batch * nn * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        gershgorin_circles_kernel<<<grid, 256>>>(batch, n, da, dc);
+        g_launches.fetch_add(1);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(circles, dc, (size_t)total * 2 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(da);
+    cudaFree(dc);
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "gershgorin: %s", cudaGetErrorString(ce));
+    return MODCHOL_OK;
+}
+
+int modchol_verify_batched_f64(int64_t batch, int32_t n, const double* a, const double* l,
+                               const double* e, const uint64_t* p, double* resid, int32_t* flags,
+                               int mem_kind, void* stream)
+{
+    g_err.clear();
+    if (batch < 0 || n < 1 || (batch > 0 && (!a || !l || !e || !p)))
+        return fail(MODCHOL_ERR_BAD_ARG, "bad argument");
+    if (n > MODCHOL_MAX_N)
+        return fail(MODCHOL_ERR_UNSUPPORTED, "n too large");
+    if (device_count() < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (batch == 0)
+        return MODCHOL_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    const unsigned grid = (unsigned)std::min<long long>(batch, (long long)g_ctx[dev].sms * 8);
+    auto pu = reinterpret_cast<const unsigned long long*>(p);
+    if (mem_kind == MODCHOL_MEM_DEVICE) {
+        verify_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(batch, n, a, l, e, pu, resid, flags);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+        return MODCHOL_OK;
+    }
+    if (mem_kind != MODCHOL_MEM_HOST)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown mem_kind %d", mem_kind);
+    const size_t nn = (size_t)n * n;
+    double *da = nullptr, *dl = nullptr, *de = nullptr, *dr = nullptr;
+    unsigned long long* dp = nullptr;
+    int* df = nullptr;
+    cudaError_t ce = cudaMalloc(&da, batch * nn * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&dl, batch * nn * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&de, (size_t)batch * n * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&dp, (size_t)batch * n * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&dr, (size_t)batch * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&df, (size_t)batch * 4);
+    if (ce == cudaSuccess) ce = cudaMemcpy(da, a, batch * nn * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(dl, l, batch * nn * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(de, e, (size_t)batch * n * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(dp, p, (size_t)batch * n * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        verify_kernel<<<grid, 256>>>(batch, n, da, dl, de, dp, dr, df);
+        g_launches.fetch_add(1);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess && resid) ce = cudaMemcpy(resid, dr, (size_t)batch * 8, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && flags) ce = cudaMemcpy(flags, df, (size_t)batch * 4, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(dl); cudaFree(de); cudaFree(dp); cudaFree(dr); cudaFree(df);
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "verify: %s", cudaGetErrorString(ce));
+    return MODCHOL_OK;
+}
+
+}  // extern "C"
