@@ -1,20 +1,28 @@
-"""In-tree build of the CUDA extension (explicit nvcc, sm_100a only)."""
+"""In-tree build of the CUDA extension (explicit nvcc, sm_100a only, objects in parallel)."""
 from __future__ import annotations
 
 import glob
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libmodchol_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",          # no implicit contraction anywhere; FAST kernels fuse explicitly
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
+]
+
+# (source, object name, extra defines)
+UNITS = [("modchol_api.cu", "api.o", [])] + [
+    ("warp_inst.cu", f"warp_a{a}_s{s}.o", [f"-DMODCHOL_INST_ALGO={a}", f"-DMODCHOL_INST_STRICT={s}"])
+    for a in (1, 2) for s in (1, 0)
 ]
 
 
@@ -27,7 +35,8 @@ def nvcc() -> str:
 
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))
-                  + [os.path.join(os.path.dirname(_HERE), "include", "modchol_b200.h")])
+                  + [os.path.join(os.path.dirname(_HERE), "include", "modchol_b200.h"),
+                     os.path.abspath(__file__)])
 
 
 def is_stale() -> bool:
@@ -37,13 +46,38 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB, os.path.join(CSRC, "modchol_api.cu")]
+def _env():
     env = dict(os.environ)
     env.pop("CC", None)   # $CC may point at a gcc without the full runtime; nvcc finds g++ itself
     env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
+    return env
+
+
+def build_library(force: bool = False, verbose: bool = False, jobs: int | None = None) -> str:
+    if not force and not is_stale():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    exe, env = nvcc(), _env()
+
+    def compile_one(unit):
+        src, obj, defs = unit
+        cmd = [exe] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + [
+            "-c", "-o", os.path.join(OBJ, obj), os.path.join(CSRC, src)]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {obj}:\n{r.stdout}\n{r.stderr}")
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=jobs or min(len(UNITS), os.cpu_count() or 4)) as ex:
+        logs = list(ex.map(compile_one, UNITS))
+    if verbose:
+        for obj, log in logs:
+            print(f"==== {obj}\n{log}")
+    subprocess.check_call([exe, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [os.path.join(OBJ, u[1]) for u in UNITS], env=env)
     return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    build_library(force=True, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,183 @@
+// warp_common.cuh -- building blocks of the warp-per-matrix, register-resident kernels.
+//
+// Layout (one warp = one matrix, NMAX <= 32):
+//   lane i owns ORIGINAL row i for the whole factorisation (rows are never moved: the
+//   symmetric row swap of utils.rs:41-49 is implicit in `pos`, the permuted position of the
+//   lane's row);   r[c] = current element (row of this lane, permuted COLUMN position c),
+//   so the column swap of utils.rs:30-38 is a physical exchange of two registers in every
+//   lane, selected by a warp-uniform switch (no dynamic register indexing, no local memory).
+//   dg = current diagonal element of the lane's row (r[pos] would need a dynamic index).
+// Measured on B200 (tools/microbench.cu): FP64 pipe 2 warp-instr/clk/SM, fmax/DSETP on
+// doubles 0.43-0.63, SHFL and REDUX 1.0, broadcast LDS.64 ~1.0.  Hence: pivot searches run
+// on order-preserving integer keys with REDUX instead of FP64 compares + shuffles, and the
+// pivot column is broadcast through a 256-byte shared-memory line instead of shuffles.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace modchol {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int I, int End, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < End) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, End>(static_cast<F&&>(f));
+    }
+}
+
+// ---- order-preserving 64-bit keys -------------------------------------------------------
+// (khi signed, klo unsigned) compares lexicographically like the double it came from;
+// -0 is folded onto +0 (IEEE `>` treats them as equal, utils.rs:63).
+__device__ __forceinline__ void make_key(double v, int& khi, unsigned& klo)
+{
+    const int hi = __double2hiint(v);
+    const unsigned lo = (unsigned)__double2loint(v);
+    const int mask = hi >> 31;
+    khi = hi ^ (mask & 0x7fffffff);
+    klo = lo ^ (unsigned)mask;
+    if (khi == -1 && klo == 0xffffffffu) {  // -0.0
+        khi = 0;
+        klo = 0u;
+    }
+}
+__device__ __forceinline__ double key_value(int khi, unsigned klo)
+{
+    const int mask = khi >> 31;
+    return __hiloint2double(khi ^ (mask & 0x7fffffff), (int)(klo ^ (unsigned)mask));
+}
+
+// Extreme (max or min) of v over the lanes with `cand`, NaN lanes never taken -- the
+// semantics of the reference's `if x > acc {x} else {acc}` folds and of utils.rs:52-70.
+// Returns the extreme value (`none` if no lane qualifies); `win` = this lane attains it.
+template <bool kMax>
+__device__ __forceinline__ double warp_extreme(double v, bool cand, double none, bool& win)
+{
+    int khi;
+    unsigned klo;
+    make_key(v, khi, klo);
+    cand = cand && (v == v);
+    if (!kMax) {
+        khi = ~khi;
+        klo = ~klo;
+    }
+    const int INT_MIN_ = (int)0x80000000;
+    const int mh = __reduce_max_sync(kFull, cand ? khi : INT_MIN_);
+    const bool c1 = cand && (khi == mh);
+    const unsigned ml = __reduce_max_sync(kFull, c1 ? klo : 0u);
+    win = c1 && (klo == ml);
+    if (mh == INT_MIN_)
+        return none;
+    return kMax ? key_value(mh, ml) : key_value(~mh, ~ml);
+}
+
+// First-strict-maximum pivot search (utils.rs:52-91) over the lanes with `active`, in
+// permuted-position order: returns the POSITION of the winner (lowest position among equal
+// maxima; a NaN at position `lo` sticks; all-NaN -> lo).  `best` receives the maximum.
+__device__ __forceinline__ int warp_argmax_first(double v, bool active, int pos, int lo,
+                                                 double& best)
+{
+    bool win;
+    best = warp_extreme<true>(v, active, -INFINITY, win);
+    int m = (int)__reduce_min_sync(kFull, win ? (unsigned)pos : 1024u);
+    const unsigned head_nan = __ballot_sync(kFull, active && pos == lo && (v != v));
+    if (head_nan || m > 255)
+        m = lo;
+    return m;
+}
+
+// ---- warp-uniform column exchange r[J] <-> r[m], m in (J, NMAX) --------------------------
+// The exchange is an opaque in-place asm block: written as plain C++ assignments, every case
+// of the switch makes ptxas materialise a fresh copy of the WHOLE register-resident matrix at
+// the join (measured: 18k SASS instructions / 134 registers versus 6.6k / 72 for a toy kernel).
+__device__ __forceinline__ void swap_in_place(double& a, double& b)
+{
+    asm volatile("{\n .reg .f64 t;\n mov.f64 t, %0;\n mov.f64 %0, %1;\n mov.f64 %1, t;\n}"
+                 : "+d"(a), "+d"(b));
+}
+#define MODCHOL_SWAP_CASE(o)                              \
+    case o:                                               \
+        if constexpr (J + 1 + (o) < NMAX)                 \
+            swap_in_place(r[J], r[J + 1 + (o)]);          \
+        break;
+
+template <int J, int NMAX>
+__device__ __forceinline__ void swap_columns_uniform(double (&r)[NMAX], int m)
+{
+    switch (m - J - 1) {
+        MODCHOL_SWAP_CASE(0) MODCHOL_SWAP_CASE(1) MODCHOL_SWAP_CASE(2) MODCHOL_SWAP_CASE(3)
+        MODCHOL_SWAP_CASE(4) MODCHOL_SWAP_CASE(5) MODCHOL_SWAP_CASE(6) MODCHOL_SWAP_CASE(7)
+        MODCHOL_SWAP_CASE(8) MODCHOL_SWAP_CASE(9) MODCHOL_SWAP_CASE(10) MODCHOL_SWAP_CASE(11)
+        MODCHOL_SWAP_CASE(12) MODCHOL_SWAP_CASE(13) MODCHOL_SWAP_CASE(14) MODCHOL_SWAP_CASE(15)
+        MODCHOL_SWAP_CASE(16) MODCHOL_SWAP_CASE(17) MODCHOL_SWAP_CASE(18) MODCHOL_SWAP_CASE(19)
+        MODCHOL_SWAP_CASE(20) MODCHOL_SWAP_CASE(21) MODCHOL_SWAP_CASE(22) MODCHOL_SWAP_CASE(23)
+        MODCHOL_SWAP_CASE(24) MODCHOL_SWAP_CASE(25) MODCHOL_SWAP_CASE(26) MODCHOL_SWAP_CASE(27)
+        MODCHOL_SWAP_CASE(28) MODCHOL_SWAP_CASE(29) MODCHOL_SWAP_CASE(30)
+    default:
+        break;
+    }
+}
+
+// r[c] for a warp-uniform run-time column c (used only by the 1x1 / 2x2 tails).
+template <int NMAX>
+__device__ __forceinline__ double get_col(const double (&r)[NMAX], int c)
+{
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i)
+        if (i == c)
+            v = r[i];
+    return v;
+}
+template <int NMAX>
+__device__ __forceinline__ void set_col(double (&r)[NMAX], int c, bool pred, double v)
+{
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i)
+        if (pred && i == c)
+            r[i] = v;
+}
+
+// ndarray-order (numeric_util::unrolled_fold) sum of x_0..x_{len-1}, lane t holding x_t
+// (lanes >= len must hold 0); len <= 31.  Returned to every lane.
+__device__ __forceinline__ double nd_sum_lanes(double x, int len)
+{
+    const int nch = len >> 3, tail = len & 7;
+    double p = (nch >= 1) ? x : 0.0;  // lanes 0..7: 0 + x_u == x_u (x_u >= +0 or any finite)
+    if (nch >= 2)
+        p = dadd(p, __shfl_down_sync(kFull, x, 8));
+    if (nch >= 3)
+        p = dadd(p, __shfl_down_sync(kFull, x, 16));
+    const double pair = dadd(p, __shfl_down_sync(kFull, p, 4));  // lanes 0..3: p_u + p_{u+4}
+    double acc = dadd(0.0, __shfl_sync(kFull, pair, 0));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 1));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 2));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 3));
+    const int base = nch << 3;
+    for (int i = 0; i < tail; ++i)
+        acc = dadd(acc, __shfl_sync(kFull, x, base + i));
+    return acc;
+}
+
+__device__ __forceinline__ double warp_sum_tree(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        x = dadd(x, __shfl_xor_sync(kFull, x, o));
+    return x;
+}
+
+// True when v is a positive normal number comfortably inside the range where
+// 1/sqrt(v), v*rsqrt(v) and their squares neither overflow nor lose precision; everything
+// else (<= 0, NaN, Inf, subnormal, huge) takes the STRICT formulas so that the special-value
+// behaviour of FAST mode is the reference's.
+__device__ __forceinline__ bool fast_range_ok(double v)
+{
+    const unsigned e = ((unsigned)__double2hiint(v) >> 20);  // sign + exponent
+    return e >= 0x100u && e <= 0x6ffu;                       // 2^-767 .. 2^+768, sign clear
+}
+
+}  // namespace modchol

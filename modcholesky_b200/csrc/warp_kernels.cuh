@@ -1,12 +1,44 @@
-// warp_kernels.cuh -- warp-per-matrix, register-resident kernels for n <= 32 (stub: filled
-// in by the next commit).
+// warp_kernels.cuh -- dispatch of the warp-per-matrix, register-resident kernels (n <= 32).
+// The kernels are instantiated in separate translation units (warp_inst.cu compiled once per
+// (algorithm, mode) so that the build parallelises); this header only declares the launchers.
 #pragma once
-#include "common.cuh"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
 namespace modchol {
-inline bool warp_kernel_available(int, int, int) { return false; }
-inline cudaError_t launch_warp_kernel(int, int, int, long long, const double*, double*, double*,
-                                      unsigned long long*, int*, int, cudaStream_t)
+
+constexpr int kWarpsPerBlock = 4;
+
+inline int warp_nmax(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 24 ? 24 : 32)); }
+
+inline bool warp_kernel_available(int algo, int mode, int n)
 {
+    (void)mode;
+    return n >= 1 && n <= 32 && (algo == 1 || algo == 2);
+}
+
+// defined in warp_inst.cu (one object per algorithm/mode pair): launch_warp_a<algo>_s<strict>
+#define MODCHOL_DECL_WARP(A, S)                                                                  \
+    cudaError_t launch_warp_a##A##_s##S(int n, long long batch, const double* a, double* l,      \
+                                        double* e, unsigned long long* p, int* k, int sms,       \
+                                        cudaStream_t st);
+MODCHOL_DECL_WARP(1, 1)
+MODCHOL_DECL_WARP(1, 0)
+MODCHOL_DECL_WARP(2, 1)
+MODCHOL_DECL_WARP(2, 0)
+
+inline cudaError_t launch_warp_kernel(int algo, int mode, int n, long long batch, const double* a,
+                                      double* l, double* e, unsigned long long* p, int* k, int sms,
+                                      cudaStream_t st)
+{
+    const bool strict = mode == 0;
+    if (algo == 1)
+        return strict ? launch_warp_a1_s1(n, batch, a, l, e, p, k, sms, st)
+                      : launch_warp_a1_s0(n, batch, a, l, e, p, k, sms, st);
+    if (algo == 2)
+        return strict ? launch_warp_a2_s1(n, batch, a, l, e, p, k, sms, st)
+                      : launch_warp_a2_s0(n, batch, a, l, e, p, k, sms, st);
     return cudaErrorNotSupported;
 }
+
 }  // namespace modchol
