@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract of this repo.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA arm (this repo)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
+
+Metric (BASELINE.json): matrices/s of batched f64 SE99 factorisations at n = 32.
+Workload at every N: 2^20 32x32 symmetric indefinite matrices PER GPU (weak scaling; the 8-GPU
+point is BASELINE.json configs[4], "8M 32x32 SE99 Hessians sharded across 8xB200").  A step is one
+factorisation of the resident batch: read A (8 GiB), write L, e, p (8.25 GiB) -- far larger than
+the 126 MB L2, so no flush is needed between steps.
+
+value    : matrices/s with the batch already resident in HBM (CUDA events on the launching
+           stream, barrier + synchronize on both sides, max over ranks).
+e2e      : the same metric through the public API with HOST (pinned) buffers: the C-ABI
+           stages host -> device -> host in overlapped chunks inside the timed region.
+roofline : algorithmic bytes (16 n^2 + 16 n per matrix) / kernel time,
+           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline : the CPU oracle (a C restatement of the reference; the Rust crate cannot be
+           built here) looped over a bounded sample on all host cores, rank 0, N = 1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_MAT = 32
+ALGO = "se99"
+BATCH_PER_GPU = 1 << 20
+E2E_BATCH_PER_GPU = 1 << 18
+CPU_SAMPLE = 1 << 18
+SEED = 0xC0FFEE
+ALG_BYTES = 16 * N_MAT * N_MAT + 16 * N_MAT          # 16 896 B per matrix
+
+
+def gen_batch(torch, batch, n, seed, device):
+    """Family F1: symmetric, entries ~ U[-1, 1] -- indefinite, SE99 enters
+    phase 2 at k = 0 (the Gershgorin path)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((batch, n, n), dtype=torch.float64, device=device)
+    step = 1 << 17
+    for s in range(0, batch, step):
+        a = torch.rand((min(step, batch - s), n, n), dtype=torch.float64, device=device, generator=g) * 2 - 1
+        out[s:s + a.shape[0]] = torch.tril(a) + torch.tril(a, -1).transpose(1, 2)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, scaled to
+    this batch (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(p))
+        return t["dram_bytes_per_matrix"] * BATCH_PER_GPU
+    except Exception:
+        return None
+
+
+def cpu_baseline(a_host, threads=0):
+    import oracle
+    oracle.build_oracle()
+    t0 = time.perf_counter()
+    r = oracle.factor_batched(ALGO, a_host, threads=threads)
+    dt = time.perf_counter() - t0
+    return a_host.shape[0] / dt, r.threads, dt
+
+
+def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path.  The crate is
+    Rust and cannot be compiled in this image (no rustc/cargo), so this times the oracle port
+    (oracle/modchol_oracle.c, a literal C restatement) looped over the batch on all host cores
+    -- the north-star's "ndarray path looped with rayon" stand-in."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    rng = np.random.default_rng(SEED)
+    a = rng.uniform(-1, 1, size=(CPU_SAMPLE, N_MAT, N_MAT))
+    a = np.tril(a) + np.transpose(np.tril(a, -1), (0, 2, 1))
+    for _ in range(max(args.warmup, 1)):
+        cpu_baseline(a[: CPU_SAMPLE // 8])
+    t0 = time.perf_counter()
+    threads = 1
+    for _ in range(args.steps):
+        _, threads, _ = cpu_baseline(a)
+    dt = time.perf_counter() - t0
+    value = args.steps * CPU_SAMPLE / dt
+    line = {
+        "impl": "reference", "metric": "matrices_per_sec", "value": value, "unit": "matrices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"se99 n={N_MAT} symmetric-uniform, {CPU_SAMPLE} matrices per step "
+                               f"(bounded sample of the 2^20-per-GPU workload)", "algo": ALGO, "n": N_MAT},
+        "cpu_baseline": {"value": value, "unit": "matrices/s", "cores": threads, "kind": "port",
+                         "sample": f"{CPU_SAMPLE} matrices x {args.steps} steps, C restatement of the "
+                                   f"reference (Rust toolchain absent), pthreads over the batch"},
+        "e2e": {"value": value, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import modcholesky_b200 as m
+    from modcholesky_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = args.batch
+    a = gen_batch(torch, batch, N_MAT, SEED + rank, dev)
+    stream = torch.cuda.current_stream()
+
+    def step(mode):
+        return m.factor_batched(ALGO, a, mode=mode)
+
+    # ---- device-resident throughput ------------------------------------------------------
+    def timed(mode, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            d = step(mode)
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        l0 = m.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            d = step(mode)
+        e1.record(stream)
+        barrier()
+        launches = m.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches, clocks, d
+
+    ms, launches, clocks, d = timed(args.mode, args.steps, args.warmup, sample_clocks=True)
+    ms_per_step = ms / args.steps
+    value = world * batch / (ms_per_step * 1e-3)
+    other = "strict" if args.mode == "fast" else "fast"
+    ms_o, _, _, _ = timed(other, max(2, args.steps // 2), 1)
+    value_other = world * batch / (ms_o / max(2, args.steps // 2) * 1e-3)
+
+    # parity spot check against the oracle on rank 0 (checker only; not timed)
+    parity = None
+    if rank == 0:
+        import oracle
+        sub = a[:512].cpu().numpy()
+        ref = oracle.factor_batched(ALGO, sub, threads=0)
+        ds = m.factor_batched(ALGO, a[:512], mode="strict")
+        parity = bool(np.array_equal(ds.l.cpu().numpy(), ref.l) and np.array_equal(ds.e.cpu().numpy(), ref.e)
+                      and np.array_equal(ds.p.cpu().numpy().astype(np.uint64), ref.p))
+        resid, flags = m.verify_batched(a, d)
+        parity = parity and int(flags.max()) == 0 and float(resid.max()) <= 1e-12
+    del d
+
+    # ---- end to end through the public API with HOST (pinned) buffers -----------------------
+    eb = min(E2E_BATCH_PER_GPU, batch)
+    ah = torch.empty((eb, N_MAT, N_MAT), dtype=torch.float64, pin_memory=True)
+    ah.copy_(a[:eb])
+    lh = torch.empty_like(ah, pin_memory=True)
+    eh = torch.empty((eb, N_MAT), dtype=torch.float64, pin_memory=True)
+    ph = torch.empty((eb, N_MAT), dtype=torch.int64, pin_memory=True)
+    L = _lib.lib()
+    mode_id = _lib.mode_id(args.mode)
+
+    def e2e_step():
+        rc = L.modchol_factor_batched_f64(_lib.SE99, mode_id, eb, N_MAT, ah.data_ptr(), lh.data_ptr(),
+                                          eh.data_ptr(), ph.data_ptr(), None, _lib.MEM_HOST, None)
+        _lib.check(rc)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()                       # returns when the results are in host memory
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * eb * e2e_steps / float(dt.item())
+    h2d = eb * N_MAT * N_MAT * 8
+    d2h = eb * (N_MAT * N_MAT * 8 + N_MAT * 8 + N_MAT * 8)
+
+    # ---- roofline of the dominant (only) kernel -------------------------------------------
+    peak, peak_src = measured_peak()
+    achieved = batch * ALG_BYTES / (ms_per_step * 1e-3) / 1e9      # per GPU: one launch per step
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(),
+                "kernel": f"se_warp_kernel<SE99, NMAX=32, {args.mode}> (one launch per step)",
+                "algorithmic_bytes_per_matrix": ALG_BYTES, "peak_source": peak_src,
+                "note": "instruction-issue bound, not HBM bound: see profiles/r01_notes.md"}
+
+    line = {
+        "metric": "matrices_per_sec", "value": value, "unit": "matrices/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"se99 n={N_MAT}, {batch} symmetric-uniform indefinite matrices per GPU "
+                               f"(BASELINE.json configs[4] per-GPU slice)",
+                   "algo": ALGO, "n": N_MAT, "batch_per_gpu": batch, "mode": args.mode,
+                   "family": "F1 symmetric-uniform (phase 2 from k=0)",
+                   "l2": "inputs (8.6 GB) + outputs (8.9 GB) per step exceed the 126 MB L2; no flush needed",
+                   "sharding": "independent contiguous batch slices, one process per GPU, no collective"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "batch_per_gpu": eb, "steps": e2e_steps,
+                "path": "modchol_factor_batched_f64(mem_kind=HOST): pinned host -> 3-slot overlapped "
+                        "H2D / kernel / D2H pipeline -> pinned host"},
+        "roofline": roofline,
+        f"value_{other}_mode": value_other,
+        "parity_spot_check": parity,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sub = a[:CPU_SAMPLE].cpu().numpy()
+        v, cores, secs = cpu_baseline(sub)
+        line["cpu_baseline"] = {"value": v, "unit": "matrices/s", "cores": cores, "kind": "port",
+                                "sample": f"{sub.shape[0]} of the {batch} matrices, {secs:.1f} s wall on "
+                                          f"{cores} threads (C restatement of the reference; Rust absent)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -162,6 +162,30 @@ __device__ __forceinline__ double nd_sum_lanes(double x, int len)
     return acc;
 }
 
+// |x| on the integer pipe (fabs() of a select compiles to an FP64-pipe DADD).
+__device__ __forceinline__ double abs_bits(double x)
+{
+    return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+}
+
+// max(a, b) for b that is never NaN: `a > b ? a : b` equals f64::max / fmax (a NaN -> b) at
+// a third of the instructions of the NaN-symmetric fmax().
+__device__ __forceinline__ double max_b_not_nan(double a, double b) { return a > b ? a : b; }
+
+// 1/sqrt(v) for v already known to be a positive normal number in [2^-767, 2^768]
+// (fast_range_ok): MUFU.RSQ64H seed + one cubically convergent correction, i.e. CUDA's
+// rsqrt() without its range checks and slow path.  Error < 1 ulp.
+__device__ __forceinline__ double rsqrt_normal(double v)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    const double t = __dmul_rn(y, y);
+    const double e = __fma_rn(-t, v, 1.0);                 // 1 - v*y^2
+    const double p = __fma_rn(e, 0.375, 0.5);              // 1/2 + 3/8 e
+    const double ey = __dmul_rn(e, y);
+    return __fma_rn(p, ey, y);                             // y (1 + e/2 + 3/8 e^2)
+}
+
 __device__ __forceinline__ double warp_sum_tree(double x)
 {
 #pragma unroll

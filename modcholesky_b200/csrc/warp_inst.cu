@@ -14,7 +14,9 @@ template <int kAlgo, int NMAX, bool kStrict>
 static cudaError_t launch_one(int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
-    auto kern = se_warp_kernel<kAlgo, NMAX, kStrict, kWarpsPerBlock>;
+    // resident blocks per SM the register allocation is asked to allow (4 warps per block)
+    constexpr int kMinBlocks = NMAX >= 24 ? 4 : (NMAX >= 16 ? 5 : 6);
+    auto kern = se_warp_kernel<kAlgo, NMAX, kStrict, kWarpsPerBlock, kMinBlocks>;
     const size_t smem = (size_t)kWarpsPerBlock * se_warp_smem_doubles<NMAX, kStrict>() * sizeof(double);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
