@@ -53,8 +53,11 @@ __device__ __forceinline__ double key_value(int khi, unsigned klo)
 // Extreme (max or min) of v over the lanes with `cand`, NaN lanes never taken -- the
 // semantics of the reference's `if x > acc {x} else {acc}` folds and of utils.rs:52-70.
 // Returns the extreme value (`none` if no lane qualifies); `win` = this lane attains it.
+// `mask` is the member mask of the lane group that owns one matrix (the whole warp, or an
+// aligned half / quarter when several small matrices share a warp).
 template <bool kMax>
-__device__ __forceinline__ double warp_extreme(double v, bool cand, double none, bool& win)
+__device__ __forceinline__ double warp_extreme(unsigned mask, double v, bool cand, double none,
+                                               bool& win)
 {
     int khi;
     unsigned klo;
@@ -65,9 +68,9 @@ __device__ __forceinline__ double warp_extreme(double v, bool cand, double none,
         klo = ~klo;
     }
     const int INT_MIN_ = (int)0x80000000;
-    const int mh = __reduce_max_sync(kFull, cand ? khi : INT_MIN_);
+    const int mh = __reduce_max_sync(mask, cand ? khi : INT_MIN_);
     const bool c1 = cand && (khi == mh);
-    const unsigned ml = __reduce_max_sync(kFull, c1 ? klo : 0u);
+    const unsigned ml = __reduce_max_sync(mask, c1 ? klo : 0u);
     win = c1 && (klo == ml);
     if (mh == INT_MIN_)
         return none;
@@ -77,13 +80,13 @@ __device__ __forceinline__ double warp_extreme(double v, bool cand, double none,
 // First-strict-maximum pivot search (utils.rs:52-91) over the lanes with `active`, in
 // permuted-position order: returns the POSITION of the winner (lowest position among equal
 // maxima; a NaN at position `lo` sticks; all-NaN -> lo).  `best` receives the maximum.
-__device__ __forceinline__ int warp_argmax_first(double v, bool active, int pos, int lo,
-                                                 double& best)
+__device__ __forceinline__ int warp_argmax_first(unsigned mask, double v, bool active, int pos,
+                                                 int lo, double& best)
 {
     bool win;
-    best = warp_extreme<true>(v, active, -INFINITY, win);
-    int m = (int)__reduce_min_sync(kFull, win ? (unsigned)pos : 1024u);
-    const unsigned head_nan = __ballot_sync(kFull, active && pos == lo && (v != v));
+    best = warp_extreme<true>(mask, v, active, -INFINITY, win);
+    int m = (int)__reduce_min_sync(mask, win ? (unsigned)pos : 1024u);
+    const unsigned head_nan = __ballot_sync(mask, active && pos == lo && (v != v));
     if (head_nan || m > 255)
         m = lo;
     return m;
@@ -142,23 +145,25 @@ __device__ __forceinline__ void set_col(double (&r)[NMAX], int c, bool pred, dou
 }
 
 // ndarray-order (numeric_util::unrolled_fold) sum of x_0..x_{len-1}, lane t holding x_t
-// (lanes >= len must hold 0); len <= 31.  Returned to every lane.
-__device__ __forceinline__ double nd_sum_lanes(double x, int len)
+// (lanes >= len must hold 0); len <= G - 1, lanes counted within the group of G.  Returned to
+// every lane of the group.
+template <int G>
+__device__ __forceinline__ double nd_sum_lanes(unsigned mask, double x, int len)
 {
     const int nch = len >> 3, tail = len & 7;
     double p = (nch >= 1) ? x : 0.0;  // lanes 0..7: 0 + x_u == x_u (x_u >= +0 or any finite)
     if (nch >= 2)
-        p = dadd(p, __shfl_down_sync(kFull, x, 8));
+        p = dadd(p, __shfl_down_sync(mask, x, 8, G));
     if (nch >= 3)
-        p = dadd(p, __shfl_down_sync(kFull, x, 16));
-    const double pair = dadd(p, __shfl_down_sync(kFull, p, 4));  // lanes 0..3: p_u + p_{u+4}
-    double acc = dadd(0.0, __shfl_sync(kFull, pair, 0));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 1));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 2));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 3));
+        p = dadd(p, __shfl_down_sync(mask, x, 16, G));
+    const double pair = dadd(p, __shfl_down_sync(mask, p, 4, G));  // lanes 0..3: p_u + p_{u+4}
+    double acc = dadd(0.0, __shfl_sync(mask, pair, 0, G));
+    acc = dadd(acc, __shfl_sync(mask, pair, 1, G));
+    acc = dadd(acc, __shfl_sync(mask, pair, 2, G));
+    acc = dadd(acc, __shfl_sync(mask, pair, 3, G));
     const int base = nch << 3;
     for (int i = 0; i < tail; ++i)
-        acc = dadd(acc, __shfl_sync(kFull, x, base + i));
+        acc = dadd(acc, __shfl_sync(mask, x, base + i, G));
     return acc;
 }
 
@@ -186,11 +191,12 @@ __device__ __forceinline__ double rsqrt_normal(double v)
     return __fma_rn(p, ey, y);                             // y (1 + e/2 + 3/8 e^2)
 }
 
-__device__ __forceinline__ double warp_sum_tree(double x)
+template <int G>
+__device__ __forceinline__ double warp_sum_tree(unsigned mask, double x)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        x = dadd(x, __shfl_xor_sync(kFull, x, o));
+    for (int o = G / 2; o > 0; o >>= 1)
+        x = dadd(x, __shfl_xor_sync(mask, x, o, G));
     return x;
 }
 

@@ -24,7 +24,9 @@ static cudaError_t launch_one(int n, long long batch, const double* a, double* l
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, smem);
     if (ce != cudaSuccess) return ce;
     if (occ < 1) occ = 1;
-    long long blocks = (batch + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    constexpr int M = 32 / se_group_lanes<NMAX>();   // matrices per warp
+    const long long slots = (batch + M - 1) / M;
+    long long blocks = (slots + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;  // persistent: every warp strides over the batch
     const int vec_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(l) & 15) == 0);

@@ -15,12 +15,22 @@
 
 namespace modchol {
 
-// Per-warp shared memory (doubles): two 32-entry column lines, plus (STRICT only) a padded
-// copy of the trailing block used once per matrix by the ndarray-ordered Gershgorin sums.
+// Lanes per matrix: the smallest power of two >= NMAX.  32 / G matrices share a warp; every
+// collective runs on the group's member mask, so the scalar logic is issued once for all of
+// them.
+template <int NMAX>
+__host__ __device__ constexpr int se_group_lanes()
+{
+    return NMAX <= 8 ? 8 : (NMAX <= 16 ? 16 : 32);
+}
+
+// Per-warp shared memory (doubles): two 32-entry column lines (G entries per group), plus
+// (STRICT only) a padded copy of each lane's row used once per matrix by the ndarray-ordered
+// Gershgorin sums.
 template <int NMAX, bool kStrict>
 __host__ __device__ constexpr int se_warp_smem_doubles()
 {
-    return 64 + (kStrict ? NMAX * (NMAX + 1) : 0);
+    return 64 + (kStrict ? 32 * (NMAX + 1) : 0);
 }
 
 #define MODCHOL_ALLJ(X)                                                                        \
@@ -98,19 +108,18 @@ __device__ __forceinline__ void dispatch_write_update(double (&r)[NMAX], int j, 
 // Lower Gershgorin bounds of the trailing block starting at k (se90.rs:105-110,
 // se99.rs:125-130): g_i = l_ii - S(|l_i,k..i-1|) - S(|l_i+1..n-1,i|), S = ndarray sum.
 template <int NMAX, bool kStrict>
-__device__ __forceinline__ double gershgorin_init(const double (&r)[NMAX], double dg, int pos,
-                                                  bool valid, int lane, int k, int n, double* rows)
+__device__ __forceinline__ double gershgorin_init(unsigned mask, const double (&r)[NMAX], double dg,
+                                                  int pos, bool valid, int lane, int k, int n,
+                                                  double* rows)
 {
     if constexpr (kStrict) {
         // every lane parks its row in shared memory (stride NMAX+1: conflict-free), then walks
         // its two index ranges with run-time offsets and compile-time partial-sum slots.
-        double* row = rows + (lane < NMAX ? lane : 0) * (NMAX + 1);
-        if (lane < NMAX) {
+        double* row = rows + lane * (NMAX + 1);
 #pragma unroll
-            for (int c = 0; c < NMAX; ++c)
-                row[c] = r[c];
-        }
-        __syncwarp();
+        for (int c = 0; c < NMAX; ++c)
+            row[c] = r[c];
+        __syncwarp(mask);
         double s[2];
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
@@ -138,7 +147,7 @@ __device__ __forceinline__ double gershgorin_init(const double (&r)[NMAX], doubl
                     acc = dadd(acc, fabs(row[start + chunked + i]));
             s[part] = acc;
         }
-        __syncwarp();
+        __syncwarp(mask);
         return dsub(dsub(dg, s[0]), s[1]);
     } else {
         (void)rows;
@@ -163,36 +172,42 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                int* __restrict__ K)
 {
     extern __shared__ double sm[];
+    constexpr int G = se_group_lanes<NMAX>();   // lanes per matrix
+    constexpr int M = 32 / G;                   // matrices per warp
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / G, gl = lane % G;    // group within the warp, lane within the group
+    const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << (grp * G));
     double* my = sm + (size_t)wib * se_warp_smem_doubles<NMAX, kStrict>();
-    double* buf0 = my;        // column line, unscaled |values| (STRICT norms)
-    double* buf1 = my + 32;   // column line, scaled values (trailing update)
+    double* buf0 = my + grp * G;        // column line, unscaled |values| (STRICT norms)
+    double* buf1 = my + 32 + grp * G;   // column line, scaled values (trailing update)
     double* rows = my + 64;
-    const bool valid = lane < n;
     const size_t nn = (size_t)n * n;
     const long long nwarps = (long long)gridDim.x * kWarps;
+    const long long nslots = (batch + M - 1) / M;   // warp-sized work items
 
-    for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nwarps) {
+    for (long long slot = (long long)blockIdx.x * kWarps + wib; slot < nslots; slot += nwarps) {
+        const long long b = slot * M + grp;
+        const bool valid = gl < n && b < batch;
         // ---- load: lane i takes column i of A (== row i, A symmetric), coalesced ----------
         double r[NMAX];
-        const double* Ab = A + (size_t)b * nn + lane;
+        const double* Ab = A + (size_t)(b < batch ? b : 0) * nn + gl;
 #pragma unroll
         for (int c = 0; c < NMAX; ++c)
             r[c] = (c < n && valid) ? __ldg(Ab + c * n) : 0.0;
-        int pos = lane;          // permuted position of this lane's row
+        int pos = gl;            // permuted position of this lane's row
         double e_mine = 0.0;     // E entry of this lane's ORIGINAL index (the un-permute of
                                  // se99.rs:194-198 is free in this layout)
         double g = 0.0;          // lower Gershgorin bound (phase 2)
         double delta_prev = 0.0;
-        double dg = get_col<NMAX>(r, lane);  // current diagonal element of this lane's row
+        double dg = get_col<NMAX>(r, gl);  // current diagonal element of this lane's row
         bool win;
         // gamma = max |a_ii| folded from 0.0 (se90.rs:55-57, se99.rs:54-56)
-        const double gamma = warp_extreme<true>(fabs(dg), valid, 0.0, win);
+        const double gamma = warp_extreme<true>(gmask, fabs(dg), valid, 0.0, win);
         const double taugamma = dmul(MODCHOL_TAU, gamma);
 
         bool phase1 = true;
         int kstart = -1;
-        int j = 0;
+        int j = (b < batch) ? 0 : n;   // an idle group (batch tail) skips the loop
         while (true) {
             // ---- A: choose the pivot position m ---------------------------------------------
             const bool active = valid && pos >= j;
@@ -201,14 +216,14 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 if (j >= n)
                     break;
                 double dmax;  // se90.rs:63, se99.rs:76
-                m = warp_argmax_first(dg, active, pos, j, dmax);
+                m = warp_argmax_first(gmask, dg, active, pos, j, dmax);
                 if (kAlgo == kSE99) {  // se99.rs:62-73, tested before the pivot is applied
-                    const double dmin = warp_extreme<false>(dg, active, INFINITY, win);
+                    const double dmin = warp_extreme<false>(gmask, dg, active, INFINITY, win);
                     if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
                         phase1 = false;
                         kstart = j;
                         if (j + 1 < n)
-                            g = gershgorin_init<NMAX, kStrict>(r, dg, pos, valid, lane, j, n, rows);
+                            g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, j, n, rows);
                         continue;
                     }
                 }
@@ -216,7 +231,7 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 if (j + 2 >= n)
                     break;
                 double gmax;  // se90.rs:115, se99.rs:135
-                m = warp_argmax_first(g, active, pos, j, gmax);
+                m = warp_argmax_first(gmask, g, active, pos, j, gmax);
             }
             // ---- B: make position m the new position j (se90.rs:64-68,116-121) --------------
             const double col = dispatch_swap_read<NMAX>(r, j, m);
@@ -226,8 +241,9 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 else if (pos == m)
                     pos = j;
             }
-            const int q = __ffs(__ballot_sync(kFull, pos == j)) - 1;
-            double piv = __shfl_sync(kFull, dg, q);
+            // q = lane (within the group) that owns the pivot row
+            const int q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
+            double piv = __shfl_sync(gmask, dg, q, G);
             const bool below = valid && pos > j;
             // ---- C1 (phase 2): E_jj (se90.rs:124-131, se99.rs:144-151) ----------------------
             double normj = 0.0, acol = 0.0;
@@ -235,12 +251,12 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 acol = below ? abs_bits(col) : 0.0;
                 if constexpr (kStrict) {
                     buf0[pos] = acol;
-                    __syncwarp();
+                    __syncwarp(gmask);
                     const int len = n - j - 1;
-                    const double x = (lane < len) ? buf0[j + 1 + lane] : 0.0;
-                    normj = nd_sum_lanes(x, len);
+                    const double x = (gl < len) ? buf0[j + 1 + gl] : 0.0;
+                    normj = nd_sum_lanes<G>(gmask, x, len);
                 } else {
-                    normj = warp_sum_tree(acol);
+                    normj = warp_sum_tree<G>(gmask, acol);
                 }
                 // e_j = max(max(0, delta_prev), -l_jj + max(normj, tau*gamma)).  delta_prev is
                 // always >= +0 and never NaN, so max(0, delta_prev) == delta_prev, and the two
@@ -256,7 +272,7 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                     piv = dadd(piv, ej);
                     delta_prev = ej;
                 }
-                if (lane == q)
+                if (gl == q)
                     e_mine = ej;
             }
             // ---- D: s = sqrt(pivot), scaled column (se90.rs:84-87, se99.rs:96-99) -----------
@@ -277,13 +293,13 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 // look-ahead min_i (l_ii - l_ij^2 / l_jj) (se90.rs:70-77, se99.rs:82-89); in
                 // FAST mode that is the updated diagonal itself.
                 const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
-                const double la = warp_extreme<false>(nv, below, INFINITY, win);
+                const double la = warp_extreme<false>(gmask, nv, below, INFINITY, win);
                 const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
                 if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
                     phase1 = false;
                     kstart = j;
                     if (j + 1 < n)
-                        g = gershgorin_init<NMAX, kStrict>(r, dg, pos, valid, lane, j, n, rows);
+                        g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, j, n, rows);
                     continue;
                 }
             } else if (fabs(dsub(piv, normj)) > MODCHOL_EPS) {
@@ -294,35 +310,35 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
             }
             // ---- E: elimination step (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171)
             buf1[pos] = cs;
-            __syncwarp();
+            __syncwarp(gmask);
             if (below)
                 dg = dg_new;
-            dispatch_write_update<NMAX, kStrict>(r, j, lane == q ? s : cs, cs, buf1, n);
-            __syncwarp();
+            dispatch_write_update<NMAX, kStrict>(r, j, gl == q ? s : cs, cs, buf1, n);
+            __syncwarp(gmask);
             ++j;
         }
 
         // ---- tails ------------------------------------------------------------------------
         if (!phase1) {
             if (kAlgo == kSE99 && kstart == n - 1) {  // se99.rs:115-119
-                const int q = __ffs(__ballot_sync(kFull, valid && pos == n - 1)) - 1;
-                const double ljj = __shfl_sync(kFull, dg, q);
+                const int q = __ffs(__ballot_sync(gmask, valid && pos == n - 1) >> (grp * G)) - 1;
+                const double ljj = __shfl_sync(gmask, dg, q, G);
                 const double ej = tail1x1_e(ljj, gamma);
-                if (lane == q)
+                if (gl == q)
                     e_mine = ej;
-                set_col<NMAX>(r, n - 1, lane == q, dsqrt(dadd(ljj, ej)));
+                set_col<NMAX>(r, n - 1, gl == q, dsqrt(dadd(ljj, ej)));
             } else {
                 // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186)
-                const int qa = __ffs(__ballot_sync(kFull, valid && pos == n - 2)) - 1;
-                const int qb = __ffs(__ballot_sync(kFull, valid && pos == n - 1)) - 1;
-                double a00 = __shfl_sync(kFull, dg, qa);
-                double a11 = __shfl_sync(kFull, dg, qb);
-                const double a01 = __shfl_sync(kFull, get_col<NMAX>(r, n - 1), qa);
-                double a10 = __shfl_sync(kFull, get_col<NMAX>(r, n - 2), qb);
+                const int qa = __ffs(__ballot_sync(gmask, valid && pos == n - 2) >> (grp * G)) - 1;
+                const int qb = __ffs(__ballot_sync(gmask, valid && pos == n - 1) >> (grp * G)) - 1;
+                double a00 = __shfl_sync(gmask, dg, qa, G);
+                double a11 = __shfl_sync(gmask, dg, qb, G);
+                const double a01 = __shfl_sync(gmask, get_col<NMAX>(r, n - 1), qa, G);
+                double a10 = __shfl_sync(gmask, get_col<NMAX>(r, n - 2), qb, G);
                 double lhi, llo;
                 eigenvalues_2x2(a00, a01, a10, a11, lhi, llo);
                 const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
-                if (lane == qa || lane == qb)
+                if (gl == qa || gl == qb)
                     e_mine = en;
                 if (en > 0.0) {
                     a00 = dadd(a00, en);
@@ -331,14 +347,14 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 a00 = dsqrt(a00);
                 a10 = ddiv(a10, a00);
                 a11 = dsqrt(dsub(a11, dmul(a10, a10)));
-                set_col<NMAX>(r, n - 2, lane == qa, a00);
-                set_col<NMAX>(r, n - 2, lane == qb, a10);
-                set_col<NMAX>(r, n - 1, lane == qb, a11);
+                set_col<NMAX>(r, n - 2, gl == qa, a00);
+                set_col<NMAX>(r, n - 2, gl == qb, a10);
+                set_col<NMAX>(r, n - 1, gl == qb, a11);
             }
         }
 
         // ---- epilogue: row `pos` of L (strict upper explicitly zero), e, p ------------------
-        double* Lrow = L + (size_t)b * nn + (size_t)pos * n;
+        double* Lrow = L + (size_t)(b < batch ? b : 0) * nn + (size_t)pos * n;
         if (valid) {
             if (vec_ok) {  // n even and L 16-byte aligned
 #pragma unroll
@@ -356,10 +372,10 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                     if (c < n)
                         Lrow[c] = (c <= pos) ? r[c] : 0.0;
             }
-            E[(size_t)b * n + lane] = e_mine;
-            P[(size_t)b * n + pos] = (unsigned long long)lane;
+            E[(size_t)b * n + gl] = e_mine;
+            P[(size_t)b * n + pos] = (unsigned long long)gl;
         }
-        if (K && lane == 0)
+        if (K && gl == 0 && b < batch)
             K[b] = kstart;
     }
 }
