@@ -2,6 +2,7 @@
 // selected with -DMODCHOL_INST_ALGO={0,1,2} -DMODCHOL_INST_STRICT={0,1}.  build.py compiles
 // this file once per pair, in parallel.
 #include "warp_kernels.cuh"
+#include "warp_gmw.cuh"
 #include "warp_se.cuh"
 
 #ifndef MODCHOL_INST_ALGO
@@ -16,21 +17,31 @@ static cudaError_t launch_one(int n, long long batch, const double* a, double* l
 {
     // resident blocks per SM the register allocation is asked to allow (4 warps per block)
     constexpr int kMinBlocks = NMAX >= 24 ? 4 : (NMAX >= 16 ? 5 : 6);
-    auto kern = se_warp_kernel<kAlgo, NMAX, kStrict, kWarpsPerBlock, kMinBlocks>;
-    const size_t smem = (size_t)kWarpsPerBlock * se_warp_smem_doubles<NMAX, kStrict>() * sizeof(double);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return ce;
-    int occ = 1;
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, smem);
-    if (ce != cudaSuccess) return ce;
-    if (occ < 1) occ = 1;
     constexpr int M = 32 / se_group_lanes<NMAX>();   // matrices per warp
     const long long slots = (batch + M - 1) / M;
     long long blocks = (slots + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const long long resident = (long long)sms * occ;
-    if (blocks > resident) blocks = resident;  // persistent: every warp strides over the batch
-    const int vec_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(l) & 15) == 0);
-    kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(n, vec_ok, batch, a, l, e, p, k);
+    int occ = 1;
+    cudaError_t ce;
+    if constexpr (kAlgo == kGMW81) {
+        auto kern = gmw_warp_kernel<NMAX, kStrict, kWarpsPerBlock, kMinBlocks>;
+        const size_t smem = (size_t)kWarpsPerBlock * gmw_warp_smem_doubles<NMAX>() * sizeof(double);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, smem);
+        if (ce != cudaSuccess) return ce;
+        const long long resident = (long long)sms * (occ < 1 ? 1 : occ);
+        if (blocks > resident) blocks = resident;  // persistent: every warp strides over the batch
+        kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    } else {
+        auto kern = se_warp_kernel<kAlgo, NMAX, kStrict, kWarpsPerBlock, kMinBlocks>;
+        const size_t smem = (size_t)kWarpsPerBlock * se_warp_smem_doubles<NMAX, kStrict>() * sizeof(double);
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerBlock * 32, smem);
+        if (ce != cudaSuccess) return ce;
+        const long long resident = (long long)sms * (occ < 1 ? 1 : occ);
+        if (blocks > resident) blocks = resident;
+        const int vec_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(l) & 15) == 0);
+        kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(n, vec_ok, batch, a, l, e, p, k);
+    }
     return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ inline int warp_nmax(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 24 ? 24 
 inline bool warp_kernel_available(int algo, int mode, int n)
 {
     (void)mode;
-    return n >= 1 && n <= 32 && (algo == 1 || algo == 2);
+    return n >= 1 && n <= 32 && algo >= 0 && algo <= 2;
 }
 
 // defined in warp_inst.cu (one object per algorithm/mode pair): launch_warp_a<algo>_s<strict>
@@ -22,6 +22,8 @@ inline bool warp_kernel_available(int algo, int mode, int n)
     cudaError_t launch_warp_a##A##_s##S(int n, long long batch, const double* a, double* l,      \
                                         double* e, unsigned long long* p, int* k, int sms,       \
                                         cudaStream_t st);
+MODCHOL_DECL_WARP(0, 1)
+MODCHOL_DECL_WARP(0, 0)
 MODCHOL_DECL_WARP(1, 1)
 MODCHOL_DECL_WARP(1, 0)
 MODCHOL_DECL_WARP(2, 1)
@@ -32,6 +34,9 @@ inline cudaError_t launch_warp_kernel(int algo, int mode, int n, long long batch
                                       cudaStream_t st)
 {
     const bool strict = mode == 0;
+    if (algo == 0)
+        return strict ? launch_warp_a0_s1(n, batch, a, l, e, p, k, sms, st)
+                      : launch_warp_a0_s0(n, batch, a, l, e, p, k, sms, st);
     if (algo == 1)
         return strict ? launch_warp_a1_s1(n, batch, a, l, e, p, k, sms, st)
                       : launch_warp_a1_s0(n, batch, a, l, e, p, k, sms, st);
