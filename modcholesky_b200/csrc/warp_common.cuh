@@ -92,36 +92,66 @@ __device__ __forceinline__ int warp_argmax_first(unsigned mask, double v, bool a
     return m;
 }
 
-// ---- warp-uniform column exchange r[J] <-> r[m], m in (J, NMAX) --------------------------
-// The exchange is an opaque in-place asm block: written as plain C++ assignments, every case
-// of the switch makes ptxas materialise a fresh copy of the WHOLE register-resident matrix at
-// the join (measured: 18k SASS instructions / 134 registers versus 6.6k / 72 for a toy kernel).
-__device__ __forceinline__ void swap_in_place(double& a, double& b)
+// ---- column exchange j <-> m with a register copy of column j ---------------------------
+// The kernels keep `cj`, a register copy of the CURRENT content of column j (it falls out of
+// the previous step's update for free).  Exchanging columns j and m (m > j, group-uniform) is
+// then a single-level switch on m:   col = r[m];  r[m] = cj;   and the physical r[j] is not
+// touched -- the elimination step overwrites it anyway.  (A first version dispatched on the
+// pair (j, m): 496 cases, 63 KB of code, two instruction-cache misses per step.)
+// The overwrite is an in-place asm: written as a plain assignment, every case of the switch
+// makes ptxas materialise a fresh copy of the WHOLE register-resident matrix at the join.
+__device__ __forceinline__ void overwrite_in_place(double& dst, double v)
 {
-    asm volatile("{\n .reg .f64 t;\n mov.f64 t, %0;\n mov.f64 %0, %1;\n mov.f64 %1, t;\n}"
-                 : "+d"(a), "+d"(b));
+    asm volatile("mov.f64 %0, %1;" : "+d"(dst) : "d"(v));
 }
-#define MODCHOL_SWAP_CASE(o)                              \
-    case o:                                               \
-        if constexpr (J + 1 + (o) < NMAX)                 \
-            swap_in_place(r[J], r[J + 1 + (o)]);          \
-        break;
-
-template <int J, int NMAX>
-__device__ __forceinline__ void swap_columns_uniform(double (&r)[NMAX], int m)
+// old = slot; slot = v -- in ONE asm: a separate C++ read of the slot next to the asm write
+// brings the whole-matrix copies back (toy kernel: 6552 vs 1480 SASS instructions).
+__device__ __forceinline__ double exchange_in_place(double& slot, double v)
 {
-    switch (m - J - 1) {
-        MODCHOL_SWAP_CASE(0) MODCHOL_SWAP_CASE(1) MODCHOL_SWAP_CASE(2) MODCHOL_SWAP_CASE(3)
-        MODCHOL_SWAP_CASE(4) MODCHOL_SWAP_CASE(5) MODCHOL_SWAP_CASE(6) MODCHOL_SWAP_CASE(7)
-        MODCHOL_SWAP_CASE(8) MODCHOL_SWAP_CASE(9) MODCHOL_SWAP_CASE(10) MODCHOL_SWAP_CASE(11)
-        MODCHOL_SWAP_CASE(12) MODCHOL_SWAP_CASE(13) MODCHOL_SWAP_CASE(14) MODCHOL_SWAP_CASE(15)
-        MODCHOL_SWAP_CASE(16) MODCHOL_SWAP_CASE(17) MODCHOL_SWAP_CASE(18) MODCHOL_SWAP_CASE(19)
-        MODCHOL_SWAP_CASE(20) MODCHOL_SWAP_CASE(21) MODCHOL_SWAP_CASE(22) MODCHOL_SWAP_CASE(23)
-        MODCHOL_SWAP_CASE(24) MODCHOL_SWAP_CASE(25) MODCHOL_SWAP_CASE(26) MODCHOL_SWAP_CASE(27)
-        MODCHOL_SWAP_CASE(28) MODCHOL_SWAP_CASE(29) MODCHOL_SWAP_CASE(30)
+    double old;
+    asm volatile("{\n mov.f64 %0, %1;\n mov.f64 %1, %2;\n}" : "=d"(old), "+d"(slot) : "d"(v));
+    return old;
+}
+
+#define MODCHOL_ALLC(X)                                                                        \
+    X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15)       \
+    X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30)  \
+    X(31)
+
+// returns the old r[m] and stores cj there
+template <int NMAX>
+__device__ __forceinline__ double take_column(double (&r)[NMAX], int m, double cj)
+{
+    double col = 0.0;
+#define MODCHOL_X(C)                            \
+    case C:                                     \
+        if constexpr (C < NMAX)                 \
+            col = exchange_in_place(r[C], cj);  \
+        break;
+    switch (m) {
+        MODCHOL_ALLC(MODCHOL_X)
     default:
         break;
     }
+#undef MODCHOL_X
+    return col;
+}
+
+// r[c] = v for a group-uniform run-time column c (in place, see overwrite_in_place)
+template <int NMAX>
+__device__ __forceinline__ void put_column(double (&r)[NMAX], int c, double v)
+{
+#define MODCHOL_X(C)                            \
+    case C:                                     \
+        if constexpr (C < NMAX)                 \
+            overwrite_in_place(r[C], v);        \
+        break;
+    switch (c) {
+        MODCHOL_ALLC(MODCHOL_X)
+    default:
+        break;
+    }
+#undef MODCHOL_X
 }
 
 // r[c] for a warp-uniform run-time column c (used only by the 1x1 / 2x2 tails).

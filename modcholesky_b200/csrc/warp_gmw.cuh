@@ -62,16 +62,20 @@ __device__ __forceinline__ double gmw_dot(const double (&r)[NMAX], const double*
     }
 }
 
-// dispatch: r[j] = c_ij = r[j] - dot_j  (gmw81.rs:83-85); returns c_ij
+// dispatch: r[j] = c_ij = l_ij - dot_j  (gmw81.rs:83-85), l_ij = cj (the register copy of
+// column j); returns c_ij and, through `next`, column j+1 (the next step's cj).
 template <int NMAX, bool kStrict>
-__device__ __forceinline__ double dispatch_gmw_column(double (&r)[NMAX], int j, const double* line)
+__device__ __forceinline__ double dispatch_gmw_column(double (&r)[NMAX], int j, double cj,
+                                                      const double* line, double& next)
 {
     double cij = 0.0;
 #define MODCHOL_X(J)                                                   \
     case J:                                                            \
         if constexpr (J < NMAX) {                                      \
-            cij = dsub(r[J], gmw_dot<J, NMAX, kStrict>(r, line));      \
+            cij = dsub(cj, gmw_dot<J, NMAX, kStrict>(r, line));        \
             r[J] = cij;                                                \
+            if constexpr (J + 1 < NMAX)                                \
+                next = r[J + 1];                                       \
         }                                                              \
         break;
     switch (j) {
@@ -114,6 +118,7 @@ gmw_warp_kernel(int n, long long batch, const double* __restrict__ A, double* __
         double e_mine = 0.0;
         double cd = get_col<NMAX>(r, gl);   // gmw81.rs:66-67: diag(c) = diag(A)
         double dpos = 0.0, sqd = 0.0, rdpos = 0.0;
+        double cj = r[0];   // register copy of the current column j (see take_column)
 
         // gmw81.rs:49-64
         bool win;
@@ -137,9 +142,8 @@ gmw_warp_kernel(int n, long long batch, const double* __restrict__ A, double* __
             const bool active = valid && pos >= j;
             double best;
             const int m = warp_argmax_first(gmask, fabs(cd), active, pos, j, best);
-            const double col = dispatch_swap_read<NMAX>(r, j, m);
-            (void)col;
             if (m != j) {
+                cj = take_column<NMAX>(r, m, cj);   // cj = r[m]; r[m] = old column j
                 if (pos == j)
                     pos = m;
                 else if (pos == m)
@@ -168,7 +172,9 @@ gmw_warp_kernel(int n, long long batch, const double* __restrict__ A, double* __
             }
             __syncwarp(gmask);
             // ---- c_ij = l_ij - sum_s l_js c_is (gmw81.rs:83-85) ------------------------------
-            const double cij = dispatch_gmw_column<NMAX, kStrict>(r, j, lline);
+            double cnext = 0.0;
+            const double cij = dispatch_gmw_column<NMAX, kStrict>(r, j, cj, lline, cnext);
+            cj = cnext;
             // theta = max_{i>j} |c_ij|, 0 for the last column (gmw81.rs:87-100)
             const double theta = warp_extreme<true>(gmask, fabs(cij), below, 0.0, win);
             const double cjj = __shfl_sync(gmask, cij, q, G);

@@ -38,28 +38,6 @@ __host__ __device__ constexpr int se_warp_smem_doubles()
     X(16) X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30)  \
     X(31)
 
-// dispatch 1: r[j] <-> r[m] (if m != j), then col = r[j]
-template <int NMAX>
-__device__ __forceinline__ double dispatch_swap_read(double (&r)[NMAX], int j, int m)
-{
-    double col = 0.0;
-#define MODCHOL_X(J)                                   \
-    case J:                                            \
-        if constexpr (J < NMAX) {                      \
-            if (m != J)                                \
-                swap_columns_uniform<J, NMAX>(r, m);   \
-            col = r[J];                                \
-        }                                              \
-        break;
-    switch (j) {
-        MODCHOL_ALLJ(MODCHOL_X)
-    default:
-        break;
-    }
-#undef MODCHOL_X
-    return col;
-}
-
 // r[k] -= cs * line[k] for k = J+1 .. n-1 (line = scaled pivot column in position order);
 // columns go in groups of eight so that padding groups (k >= n) are skipped.
 template <int J, int NMAX, bool kStrict>
@@ -86,15 +64,19 @@ __device__ __forceinline__ void trailing_update(double (&r)[NMAX], double cs, co
 
 // dispatch 2: r[j] = newj (sqrt of the pivot in the pivot lane, scaled column elsewhere),
 // then the trailing update of se90.rs:88-92 / se99.rs:100-104.
+// Returns the updated column j+1 (the next step's `cj`).
 template <int NMAX, bool kStrict>
-__device__ __forceinline__ void dispatch_write_update(double (&r)[NMAX], int j, double newj,
-                                                      double cs, const double* line, int n)
+__device__ __forceinline__ double dispatch_write_update(double (&r)[NMAX], int j, double newj,
+                                                        double cs, const double* line, int n)
 {
+    double next = 0.0;
 #define MODCHOL_X(J)                                             \
     case J:                                                      \
         if constexpr (J < NMAX) {                                \
             r[J] = newj;                                         \
             trailing_update<J, NMAX, kStrict>(r, cs, line, n);   \
+            if constexpr (J + 1 < NMAX)                          \
+                next = r[J + 1];                                 \
         }                                                        \
         break;
     switch (j) {
@@ -103,6 +85,7 @@ __device__ __forceinline__ void dispatch_write_update(double (&r)[NMAX], int j, 
         break;
     }
 #undef MODCHOL_X
+    return next;
 }
 
 // Lower Gershgorin bounds of the trailing block starting at k (se90.rs:105-110,
@@ -205,6 +188,7 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
         const double gamma = warp_extreme<true>(gmask, fabs(dg), valid, 0.0, win);
         const double taugamma = dmul(MODCHOL_TAU, gamma);
 
+        double cj = r[0];        // register copy of the current column j (see take_column)
         bool phase1 = true;
         int kstart = -1;
         int j = (b < batch) ? 0 : n;   // an idle group (batch tail) skips the loop
@@ -224,7 +208,7 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                         kstart = j;
                         if (j + 1 < n)
                             g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, j, n, rows);
-                        continue;
+                        continue;   // no exchange has happened at this j: r[j] is current
                     }
                 }
             } else {
@@ -234,8 +218,10 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 m = warp_argmax_first(gmask, g, active, pos, j, gmax);
             }
             // ---- B: make position m the new position j (se90.rs:64-68,116-121) --------------
-            const double col = dispatch_swap_read<NMAX>(r, j, m);
+            double col = cj;
             if (m != j) {
+                col = take_column<NMAX>(r, m, cj);   // col = r[m]; r[m] = old column j
+                cj = col;
                 if (pos == j)
                     pos = m;
                 else if (pos == m)
@@ -298,6 +284,7 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
                     phase1 = false;
                     kstart = j;
+                    put_column<NMAX>(r, j, cj);   // materialise column j (see take_column)
                     if (j + 1 < n)
                         g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, j, n, rows);
                     continue;
@@ -313,7 +300,7 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
             __syncwarp(gmask);
             if (below)
                 dg = dg_new;
-            dispatch_write_update<NMAX, kStrict>(r, j, gl == q ? s : cs, cs, buf1, n);
+            cj = dispatch_write_update<NMAX, kStrict>(r, j, gl == q ? s : cs, cs, buf1, n);
             __syncwarp(gmask);
             ++j;
         }
