@@ -154,7 +154,34 @@ __device__ __forceinline__ void put_column(double (&r)[NMAX], int c, double v)
 #undef MODCHOL_X
 }
 
-// r[c] for a warp-uniform run-time column c (used only by the 1x1 / 2x2 tails).
+// v = r[c] for a group-uniform run-time column c, by switch (12 instructions; the select
+// chain below costs 3 per column)
+template <int NMAX>
+__device__ __forceinline__ double read_column(const double (&r)[NMAX], int c)
+{
+    double v = 0.0;
+#define MODCHOL_X(C)                \
+    case C:                         \
+        if constexpr (C < NMAX)     \
+            v = r[C];               \
+        break;
+    switch (c) {
+        MODCHOL_ALLC(MODCHOL_X)
+    default:
+        break;
+    }
+#undef MODCHOL_X
+    return v;
+}
+// r[c] = v in the lanes with pred, for a group-uniform run-time column c
+template <int NMAX>
+__device__ __forceinline__ void put_column_if(double (&r)[NMAX], int c, bool pred, double v)
+{
+    const double old = read_column<NMAX>(r, c);
+    put_column<NMAX>(r, c, pred ? v : old);
+}
+
+// r[c] for a per-lane run-time column c (select chain).
 template <int NMAX>
 __device__ __forceinline__ double get_col(const double (&r)[NMAX], int c)
 {

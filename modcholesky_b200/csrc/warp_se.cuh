@@ -136,12 +136,14 @@ __device__ __forceinline__ double gershgorin_init(unsigned mask, const double (&
         (void)rows;
         (void)lane;
         (void)valid;
+        (void)n;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int c = 0; c < NMAX; c += 2) {
-            if (c >= k && c != pos && c < n)
+            // padding columns (c >= n) hold zeros
+            if (c >= k && c != pos)
                 a0 = dadd(a0, fabs(r[c]));
-            if (c + 1 < NMAX && c + 1 >= k && c + 1 != pos && c + 1 < n)
+            if (c + 1 < NMAX && c + 1 >= k && c + 1 != pos)
                 a1 = dadd(a1, fabs(r[c + 1]));
         }
         return dsub(dg, dadd(a0, a1));
@@ -177,94 +179,40 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
 #pragma unroll
         for (int c = 0; c < NMAX; ++c)
             r[c] = (c < n && valid) ? __ldg(Ab + c * n) : 0.0;
+        const bool live = b < batch;
         int pos = gl;            // permuted position of this lane's row
         double e_mine = 0.0;     // E entry of this lane's ORIGINAL index (the un-permute of
                                  // se99.rs:194-198 is free in this layout)
         double g = 0.0;          // lower Gershgorin bound (phase 2)
         double delta_prev = 0.0;
-        double dg = get_col<NMAX>(r, gl);  // current diagonal element of this lane's row
+        // current diagonal element of this lane's row (r[pos] would need a dynamic index)
+        double dg = valid ? __ldg(Ab + gl * n) : 0.0;
         bool win;
         // gamma = max |a_ii| folded from 0.0 (se90.rs:55-57, se99.rs:54-56)
         const double gamma = warp_extreme<true>(gmask, fabs(dg), valid, 0.0, win);
         const double taugamma = dmul(MODCHOL_TAU, gamma);
 
         double cj = r[0];        // register copy of the current column j (see take_column)
-        bool phase1 = true;
         int kstart = -1;
-        int j = (b < batch) ? 0 : n;   // an idle group (batch tail) skips the loop
-        while (true) {
-            // ---- A: choose the pivot position m ---------------------------------------------
-            const bool active = valid && pos >= j;
-            int m;
-            if (phase1) {
-                if (j >= n)
-                    break;
-                double dmax;  // se90.rs:63, se99.rs:76
-                m = warp_argmax_first(gmask, dg, active, pos, j, dmax);
-                if (kAlgo == kSE99) {  // se99.rs:62-73, tested before the pivot is applied
-                    const double dmin = warp_extreme<false>(gmask, dg, active, INFINITY, win);
-                    if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
-                        phase1 = false;
-                        kstart = j;
-                        if (j + 1 < n)
-                            g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, j, n, rows);
-                        continue;   // no exchange has happened at this j: r[j] is current
-                    }
-                }
-            } else {
-                if (j + 2 >= n)
-                    break;
-                double gmax;  // se90.rs:115, se99.rs:135
-                m = warp_argmax_first(gmask, g, active, pos, j, gmax);
-            }
-            // ---- B: make position m the new position j (se90.rs:64-68,116-121) --------------
-            double col = cj;
+
+        // B: make position m the new position j (se90.rs:64-68,116-121); returns this lane's
+        // element of the pivot column
+        auto bring_pivot = [&](int j, int m) -> double {
             if (m != j) {
-                col = take_column<NMAX>(r, m, cj);   // col = r[m]; r[m] = old column j
-                cj = col;
+                cj = take_column<NMAX>(r, m, cj);   // cj = r[m]; r[m] = old column j
                 if (pos == j)
                     pos = m;
                 else if (pos == m)
                     pos = j;
             }
-            // q = lane (within the group) that owns the pivot row
-            const int q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
-            double piv = __shfl_sync(gmask, dg, q, G);
-            const bool below = valid && pos > j;
-            // ---- C1 (phase 2): E_jj (se90.rs:124-131, se99.rs:144-151) ----------------------
-            double normj = 0.0, acol = 0.0;
-            if (!phase1) {
-                acol = below ? abs_bits(col) : 0.0;
-                if constexpr (kStrict) {
-                    buf0[pos] = acol;
-                    __syncwarp(gmask);
-                    const int len = n - j - 1;
-                    const double x = (gl < len) ? buf0[j + 1 + gl] : 0.0;
-                    normj = nd_sum_lanes<G>(gmask, x, len);
-                } else {
-                    normj = warp_sum_tree<G>(gmask, acol);
-                }
-                // e_j = max(max(0, delta_prev), -l_jj + max(normj, tau*gamma)).  delta_prev is
-                // always >= +0 and never NaN, so max(0, delta_prev) == delta_prev, and the two
-                // remaining maxima have a never-NaN second operand.
-                const double ej =
-                    max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
-                if (kStrict) {
-                    if (ej > 0.0) {
-                        piv = dadd(piv, ej);
-                        delta_prev = ej;
-                    }
-                } else {  // ej >= delta_prev >= 0: adding an exact zero changes nothing
-                    piv = dadd(piv, ej);
-                    delta_prev = ej;
-                }
-                if (gl == q)
-                    e_mine = ej;
-            }
-            // ---- D: s = sqrt(pivot), scaled column (se90.rs:84-87, se99.rs:96-99) -----------
+            return cj;
+        };
+        // D: s = sqrt(pivot) and the scaled column element (se90.rs:84-87, se99.rs:96-99).
+        // FAST: y = rsqrt(piv), s = piv*y, cs = col*y, 1/piv = y*y for pivots in the safe
+        // range; everything else takes the reference's formulas.
+        auto scale = [&](double piv, double col, double& s, double& cs, double& inv_piv) -> bool {
             const bool fast = !kStrict && fast_range_ok(piv);
-            double s, cs, inv_piv = 0.0;
-            if (fast) {  // y = rsqrt(piv): s = piv*y, cs = col*y, 1/piv = y*y
+            if (fast) {
                 const double y = rsqrt_normal(piv);
                 s = dmul(piv, y);
                 cs = dmul(col, y);
@@ -272,56 +220,119 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
             } else {
                 s = dsqrt(piv);
                 cs = ddiv(col, s);
+                inv_piv = 0.0;
             }
-            const double dg_new = nmul_add<kStrict>(dg, cs, cs);
-            // ---- C2 ------------------------------------------------------------------------
-            if (phase1) {
-                // look-ahead min_i (l_ii - l_ij^2 / l_jj) (se90.rs:70-77, se99.rs:82-89); in
-                // FAST mode that is the updated diagonal itself.
-                const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
-                const double la = warp_extreme<false>(gmask, nv, below, INFINITY, win);
-                const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
-                if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
-                    phase1 = false;
-                    kstart = j;
-                    put_column<NMAX>(r, j, cj);   // materialise column j (see take_column)
-                    if (j + 1 < n)
-                        g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, j, n, rows);
-                    continue;
-                }
-            } else if (fabs(dsub(piv, normj)) > MODCHOL_EPS) {
-                // bound update (se90.rs:134-139, se99.rs:154-159)
-                const double t = fast ? __fma_rn(-normj, inv_piv, 1.0) : dsub(1.0, ddiv(normj, piv));
-                if (below)
-                    g = mul_add<kStrict>(g, acol, t);
-            }
-            // ---- E: elimination step (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171)
+            return fast;
+        };
+        // E: elimination step (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171)
+        auto eliminate = [&](int j, int q, bool below, double s, double cs, double dg_new) {
             buf1[pos] = cs;
             __syncwarp(gmask);
             if (below)
                 dg = dg_new;
             cj = dispatch_write_update<NMAX, kStrict>(r, j, gl == q ? s : cs, cs, buf1, n);
             __syncwarp(gmask);
-            ++j;
+        };
+
+        // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
+        const int nsteps = live ? n : 0;   // an idle group (batch tail) does nothing
+        for (int j = 0; j < nsteps; ++j) {
+            const bool active = valid && pos >= j;
+            double dmax;  // se90.rs:63, se99.rs:76
+            const int m = warp_argmax_first(gmask, dg, active, pos, j, dmax);
+            if (kAlgo == kSE99) {  // se99.rs:62-73, tested before the pivot is applied
+                const double dmin = warp_extreme<false>(gmask, dg, active, INFINITY, win);
+                if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
+                    kstart = j;   // no exchange has happened at this j: r[j] is current
+                    break;
+                }
+            }
+            const double col = bring_pivot(j, m);
+            const int q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
+            const double piv = __shfl_sync(gmask, dg, q, G);
+            const bool below = valid && pos > j;
+            double s, cs, inv_piv;
+            const bool fast = scale(piv, col, s, cs, inv_piv);
+            const double dg_new = nmul_add<kStrict>(dg, cs, cs);
+            // look-ahead min_i (l_ii - l_ij^2 / l_jj) (se90.rs:70-77, se99.rs:82-89); in FAST
+            // mode that is the updated diagonal itself.
+            const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
+            const double la = warp_extreme<false>(gmask, nv, below, INFINITY, win);
+            const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
+            if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
+                kstart = j;
+                put_column<NMAX>(r, j, cj);   // materialise column j (see take_column)
+                break;
+            }
+            eliminate(j, q, below, s, cs, dg_new);
         }
 
-        // ---- tails ------------------------------------------------------------------------
-        if (!phase1) {
+        // ---- phase 2 ----------------------------------------------------------------------
+        if (kstart >= 0) {
             if (kAlgo == kSE99 && kstart == n - 1) {  // se99.rs:115-119
                 const int q = __ffs(__ballot_sync(gmask, valid && pos == n - 1) >> (grp * G)) - 1;
                 const double ljj = __shfl_sync(gmask, dg, q, G);
                 const double ej = tail1x1_e(ljj, gamma);
                 if (gl == q)
                     e_mine = ej;
-                set_col<NMAX>(r, n - 1, gl == q, dsqrt(dadd(ljj, ej)));
+                put_column_if<NMAX>(r, n - 1, gl == q, dsqrt(dadd(ljj, ej)));
             } else {
+                g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, kstart, n, rows);
+                for (int j = kstart; j + 2 < n; ++j) {
+                    const bool active = valid && pos >= j;
+                    double gmax;  // se90.rs:115, se99.rs:135
+                    const int m = warp_argmax_first(gmask, g, active, pos, j, gmax);
+                    const double col = bring_pivot(j, m);
+                    const int q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
+                    double piv = __shfl_sync(gmask, dg, q, G);
+                    const bool below = valid && pos > j;
+                    // E_jj (se90.rs:124-131, se99.rs:144-151)
+                    const double acol = below ? abs_bits(col) : 0.0;
+                    double normj;
+                    if constexpr (kStrict) {
+                        buf0[pos] = acol;
+                        __syncwarp(gmask);
+                        const int len = n - j - 1;
+                        const double x = (gl < len) ? buf0[j + 1 + gl] : 0.0;
+                        normj = nd_sum_lanes<G>(gmask, x, len);
+                    } else {
+                        normj = warp_sum_tree<G>(gmask, acol);
+                    }
+                    // e_j = max(max(0, delta_prev), -l_jj + max(normj, tau*gamma)).  delta_prev
+                    // is always >= +0 and never NaN, so max(0, delta_prev) == delta_prev, and
+                    // the two remaining maxima have a never-NaN second operand.
+                    const double ej =
+                        max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
+                    if (kStrict) {
+                        if (ej > 0.0) {
+                            piv = dadd(piv, ej);
+                            delta_prev = ej;
+                        }
+                    } else {  // ej >= delta_prev >= 0: adding an exact zero changes nothing
+                        piv = dadd(piv, ej);
+                        delta_prev = ej;
+                    }
+                    if (gl == q)
+                        e_mine = ej;
+                    double s, cs, inv_piv;
+                    const bool fast = scale(piv, col, s, cs, inv_piv);
+                    const double dg_new = nmul_add<kStrict>(dg, cs, cs);
+                    // bound update (se90.rs:134-139, se99.rs:154-159)
+                    if (fabs(dsub(piv, normj)) > MODCHOL_EPS) {
+                        const double t =
+                            fast ? __fma_rn(-normj, inv_piv, 1.0) : dsub(1.0, ddiv(normj, piv));
+                        if (below)
+                            g = mul_add<kStrict>(g, acol, t);
+                    }
+                    eliminate(j, q, below, s, cs, dg_new);
+                }
                 // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186)
                 const int qa = __ffs(__ballot_sync(gmask, valid && pos == n - 2) >> (grp * G)) - 1;
                 const int qb = __ffs(__ballot_sync(gmask, valid && pos == n - 1) >> (grp * G)) - 1;
                 double a00 = __shfl_sync(gmask, dg, qa, G);
                 double a11 = __shfl_sync(gmask, dg, qb, G);
-                const double a01 = __shfl_sync(gmask, get_col<NMAX>(r, n - 1), qa, G);
-                double a10 = __shfl_sync(gmask, get_col<NMAX>(r, n - 2), qb, G);
+                const double a01 = __shfl_sync(gmask, read_column<NMAX>(r, n - 1), qa, G);
+                double a10 = __shfl_sync(gmask, read_column<NMAX>(r, n - 2), qb, G);
                 double lhi, llo;
                 eigenvalues_2x2(a00, a01, a10, a11, lhi, llo);
                 const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
@@ -334,9 +345,8 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                 a00 = dsqrt(a00);
                 a10 = ddiv(a10, a00);
                 a11 = dsqrt(dsub(a11, dmul(a10, a10)));
-                set_col<NMAX>(r, n - 2, gl == qa, a00);
-                set_col<NMAX>(r, n - 2, gl == qb, a10);
-                set_col<NMAX>(r, n - 1, gl == qb, a11);
+                put_column_if<NMAX>(r, n - 2, gl == qa || gl == qb, gl == qa ? a00 : a10);
+                put_column_if<NMAX>(r, n - 1, gl == qb, a11);
             }
         }
 
@@ -362,7 +372,7 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
             E[(size_t)b * n + gl] = e_mine;
             P[(size_t)b * n + pos] = (unsigned long long)gl;
         }
-        if (K && gl == 0 && b < batch)
+        if (K && gl == 0 && live)
             K[b] = kstart;
     }
 }
