@@ -59,8 +59,11 @@ def build_library(force: bool = False, verbose: bool = False, jobs: int | None =
     os.makedirs(OBJ, exist_ok=True)
     exe, env = nvcc(), _env()
 
+    extra = os.environ.get("MODCHOL_NVCC_EXTRA", "").split()   # experiments, e.g. -DMODCHOL_MINB32=5
+
     def compile_one(unit):
         src, obj, defs = unit
+        defs = defs + extra
         cmd = [exe] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", "-o", os.path.join(OBJ, obj), os.path.join(CSRC, src)]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True)

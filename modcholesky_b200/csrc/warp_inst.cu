@@ -5,6 +5,9 @@
 #include "warp_gmw.cuh"
 #include "warp_se.cuh"
 
+#ifndef MODCHOL_MINB32
+#define MODCHOL_MINB32 4   /* resident 4-warp blocks per SM asked of ptxas for NMAX >= 24 */
+#endif
 #ifndef MODCHOL_INST_ALGO
 #error "compile with -DMODCHOL_INST_ALGO=.. -DMODCHOL_INST_STRICT=.."
 #endif
@@ -16,7 +19,7 @@ static cudaError_t launch_one(int n, long long batch, const double* a, double* l
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
     // resident blocks per SM the register allocation is asked to allow (4 warps per block)
-    constexpr int kMinBlocks = NMAX >= 24 ? 4 : (NMAX >= 16 ? 5 : 6);
+    constexpr int kMinBlocks = NMAX >= 24 ? MODCHOL_MINB32 : (NMAX >= 16 ? 5 : 6);
     constexpr int M = 32 / se_group_lanes<NMAX>();   // matrices per warp
     const long long slots = (batch + M - 1) / M;
     long long blocks = (slots + kWarpsPerBlock - 1) / kWarpsPerBlock;

@@ -224,50 +224,113 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
             }
             return fast;
         };
-        // E: elimination step (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171)
-        auto eliminate = [&](int j, int q, bool below, double s, double cs, double dg_new) {
+        // ---- one loop over the step j; the scalar part is phase specific and straight-line, the
+        //      elimination step (the big switch dispatch) exists once for both phases ----------
+        bool phase1 = true;
+        int j = 0;
+        const int nsteps = live ? n : 0;   // an idle group (batch tail) does nothing
+        while (true) {
+            int q;
+            bool below;
+            double s, cs, dg_new;
+            if (phase1) {
+                // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) ------------------------------
+                if (j >= nsteps)
+                    break;
+                const bool active = valid && pos >= j;
+                double dmax;  // se90.rs:63, se99.rs:76
+                const int m = warp_argmax_first(gmask, dg, active, pos, j, dmax);
+                bool to_phase2 = false;
+                if (kAlgo == kSE99) {  // se99.rs:62-73, tested before the pivot is applied
+                    const double dmin = warp_extreme<false>(gmask, dg, active, INFINITY, win);
+                    to_phase2 = dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax);
+                }
+                if (!to_phase2) {
+                    const double col = bring_pivot(j, m);
+                    q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
+                    const double piv = __shfl_sync(gmask, dg, q, G);
+                    below = valid && pos > j;
+                    double inv_piv;
+                    const bool fast = scale(piv, col, s, cs, inv_piv);
+                    dg_new = nmul_add<kStrict>(dg, cs, cs);
+                    // look-ahead min_i (l_ii - l_ij^2 / l_jj) (se90.rs:70-77, se99.rs:82-89);
+                    // in FAST mode that is the updated diagonal itself.
+                    const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
+                    const double la = warp_extreme<false>(gmask, nv, below, INFINITY, win);
+                    const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
+                    if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
+                        to_phase2 = true;
+                        put_column<NMAX>(r, j, cj);   // materialise column j (see take_column)
+                    }
+                }
+                if (to_phase2) {
+                    phase1 = false;
+                    kstart = j;
+                    if (!(kAlgo == kSE99 && kstart == n - 1))
+                        g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, kstart, n, rows);
+                    continue;
+                }
+            } else {
+                // ---- phase 2 step (se90.rs:113-152, se99.rs:133-172) -----------------------
+                if (j + 2 >= n)
+                    break;
+                const bool active = valid && pos >= j;
+                double gmax;  // se90.rs:115, se99.rs:135
+                const int m = warp_argmax_first(gmask, g, active, pos, j, gmax);
+                const double col = bring_pivot(j, m);
+                q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
+                double piv = __shfl_sync(gmask, dg, q, G);
+                below = valid && pos > j;
+                // E_jj (se90.rs:124-131, se99.rs:144-151)
+                const double acol = below ? abs_bits(col) : 0.0;
+                double normj;
+                if constexpr (kStrict) {
+                    buf0[pos] = acol;
+                    __syncwarp(gmask);
+                    const int len = n - j - 1;
+                    const double x = (gl < len) ? buf0[j + 1 + gl] : 0.0;
+                    normj = nd_sum_lanes<G>(gmask, x, len);
+                } else {
+                    normj = warp_sum_tree<G>(gmask, acol);
+                }
+                // e_j = max(max(0, delta_prev), -l_jj + max(normj, tau*gamma)).  delta_prev is
+                // always >= +0 and never NaN, so max(0, delta_prev) == delta_prev, and the two
+                // remaining maxima have a never-NaN second operand.
+                const double ej =
+                    max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
+                if (kStrict) {
+                    if (ej > 0.0) {
+                        piv = dadd(piv, ej);
+                        delta_prev = ej;
+                    }
+                } else {  // ej >= delta_prev >= 0: adding an exact zero changes nothing
+                    piv = dadd(piv, ej);
+                    delta_prev = ej;
+                }
+                if (gl == q)
+                    e_mine = ej;
+                double inv_piv;
+                const bool fast = scale(piv, col, s, cs, inv_piv);
+                dg_new = nmul_add<kStrict>(dg, cs, cs);
+                // bound update (se90.rs:134-139, se99.rs:154-159)
+                if (fabs(dsub(piv, normj)) > MODCHOL_EPS) {
+                    const double t =
+                        fast ? __fma_rn(-normj, inv_piv, 1.0) : dsub(1.0, ddiv(normj, piv));
+                    if (below)
+                        g = mul_add<kStrict>(g, acol, t);
+                }
+            }
+            // ---- elimination step (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171) ----
             buf1[pos] = cs;
             __syncwarp(gmask);
             if (below)
                 dg = dg_new;
             cj = dispatch_write_update<NMAX, kStrict>(r, j, gl == q ? s : cs, cs, buf1, n);
             __syncwarp(gmask);
-        };
-
-        // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
-        const int nsteps = live ? n : 0;   // an idle group (batch tail) does nothing
-        for (int j = 0; j < nsteps; ++j) {
-            const bool active = valid && pos >= j;
-            double dmax;  // se90.rs:63, se99.rs:76
-            const int m = warp_argmax_first(gmask, dg, active, pos, j, dmax);
-            if (kAlgo == kSE99) {  // se99.rs:62-73, tested before the pivot is applied
-                const double dmin = warp_extreme<false>(gmask, dg, active, INFINITY, win);
-                if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
-                    kstart = j;   // no exchange has happened at this j: r[j] is current
-                    break;
-                }
-            }
-            const double col = bring_pivot(j, m);
-            const int q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
-            const double piv = __shfl_sync(gmask, dg, q, G);
-            const bool below = valid && pos > j;
-            double s, cs, inv_piv;
-            const bool fast = scale(piv, col, s, cs, inv_piv);
-            const double dg_new = nmul_add<kStrict>(dg, cs, cs);
-            // look-ahead min_i (l_ii - l_ij^2 / l_jj) (se90.rs:70-77, se99.rs:82-89); in FAST
-            // mode that is the updated diagonal itself.
-            const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
-            const double la = warp_extreme<false>(gmask, nv, below, INFINITY, win);
-            const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
-            if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
-                kstart = j;
-                put_column<NMAX>(r, j, cj);   // materialise column j (see take_column)
-                break;
-            }
-            eliminate(j, q, below, s, cs, dg_new);
+            ++j;
         }
 
-        // ---- phase 2 ----------------------------------------------------------------------
+        // ---- tails ------------------------------------------------------------------------
         if (kstart >= 0) {
             if (kAlgo == kSE99 && kstart == n - 1) {  // se99.rs:115-119
                 const int q = __ffs(__ballot_sync(gmask, valid && pos == n - 1) >> (grp * G)) - 1;
@@ -277,55 +340,6 @@ se_warp_kernel(int n, int vec_ok, long long batch, const double* __restrict__ A,
                     e_mine = ej;
                 put_column_if<NMAX>(r, n - 1, gl == q, dsqrt(dadd(ljj, ej)));
             } else {
-                g = gershgorin_init<NMAX, kStrict>(gmask, r, dg, pos, valid, lane, kstart, n, rows);
-                for (int j = kstart; j + 2 < n; ++j) {
-                    const bool active = valid && pos >= j;
-                    double gmax;  // se90.rs:115, se99.rs:135
-                    const int m = warp_argmax_first(gmask, g, active, pos, j, gmax);
-                    const double col = bring_pivot(j, m);
-                    const int q = __ffs(__ballot_sync(gmask, pos == j) >> (grp * G)) - 1;
-                    double piv = __shfl_sync(gmask, dg, q, G);
-                    const bool below = valid && pos > j;
-                    // E_jj (se90.rs:124-131, se99.rs:144-151)
-                    const double acol = below ? abs_bits(col) : 0.0;
-                    double normj;
-                    if constexpr (kStrict) {
-                        buf0[pos] = acol;
-                        __syncwarp(gmask);
-                        const int len = n - j - 1;
-                        const double x = (gl < len) ? buf0[j + 1 + gl] : 0.0;
-                        normj = nd_sum_lanes<G>(gmask, x, len);
-                    } else {
-                        normj = warp_sum_tree<G>(gmask, acol);
-                    }
-                    // e_j = max(max(0, delta_prev), -l_jj + max(normj, tau*gamma)).  delta_prev
-                    // is always >= +0 and never NaN, so max(0, delta_prev) == delta_prev, and
-                    // the two remaining maxima have a never-NaN second operand.
-                    const double ej =
-                        max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
-                    if (kStrict) {
-                        if (ej > 0.0) {
-                            piv = dadd(piv, ej);
-                            delta_prev = ej;
-                        }
-                    } else {  // ej >= delta_prev >= 0: adding an exact zero changes nothing
-                        piv = dadd(piv, ej);
-                        delta_prev = ej;
-                    }
-                    if (gl == q)
-                        e_mine = ej;
-                    double s, cs, inv_piv;
-                    const bool fast = scale(piv, col, s, cs, inv_piv);
-                    const double dg_new = nmul_add<kStrict>(dg, cs, cs);
-                    // bound update (se90.rs:134-139, se99.rs:154-159)
-                    if (fabs(dsub(piv, normj)) > MODCHOL_EPS) {
-                        const double t =
-                            fast ? __fma_rn(-normj, inv_piv, 1.0) : dsub(1.0, ddiv(normj, piv));
-                        if (below)
-                            g = mul_add<kStrict>(g, acol, t);
-                    }
-                    eliminate(j, q, below, s, cs, dg_new);
-                }
                 // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186)
                 const int qa = __ffs(__ballot_sync(gmask, valid && pos == n - 2) >> (grp * G)) - 1;
                 const int qb = __ffs(__ballot_sync(gmask, valid && pos == n - 1) >> (grp * G)) - 1;
