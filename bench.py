@@ -289,7 +289,7 @@ def main():
                 "frac": achieved / peak, "traffic": ncu_traffic(),
                 "kernel": f"se_warp_kernel<SE99, NMAX=32, {args.mode}> (one launch per step)",
                 "algorithmic_bytes_per_matrix": ALG_BYTES, "peak_source": peak_src,
-                "note": "instruction-issue bound, not HBM bound: see profiles/r01_notes.md"}
+                "note": "per-warp latency bound (7.4 cycles per issued instruction, 16 matrices per SM), not HBM bound: see profiles/r01_notes.md"}
 
     line = {
         "metric": "matrices_per_sec", "value": value, "unit": "matrices/s", "n_gpus": world,
