@@ -113,6 +113,12 @@ int modchol_verify_batched_f64(int64_t batch, int32_t n, const double *a, const 
  * "cta_smem", "cta_gmem" -- for logging and tests.  Never NULL. */
 const char *modchol_kernel_class(int algo, int mode, int32_t n);
 
+/* Tuning knob: which small-n kernel family serves n <= 32 for SE90/SE99 -- 0 = automatic
+ * (register-resident "warp32"), 1 = register-resident, 2 = shared-memory-resident
+ * ("warp_smem", always used for 32 < n <= 64).  Returns the previous setting.  Both families
+ * produce identical STRICT results; the knob exists for benchmarking and tests. */
+int modchol_set_small_kernel_family(int family);
+
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t modchol_launch_count(void);
 

@@ -27,3 +27,10 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(lib().modchol_launch_count())
+
+
+def set_small_kernel_family(family) -> int:
+    """0/'auto', 1/'reg' (register-resident), 2/'wsm' (shared-memory-resident): which kernel family
+    serves n <= 32 for SE90/SE99.  Returns the previous setting."""
+    ids = {"auto": 0, "reg": 1, "wsm": 2}
+    return int(lib().modchol_set_small_kernel_family(ids.get(family, family)))

@@ -25,6 +25,7 @@ EXPORTS = (
     "modchol_gershgorin_circles_batched_f64",
     "modchol_verify_batched_f64",
     "modchol_kernel_class",
+    "modchol_set_small_kernel_family",
     "modchol_launch_count",
     "modchol_last_error",
     "modchol_version",
@@ -67,6 +68,8 @@ def lib() -> ctypes.CDLL:
     L.modchol_verify_batched_f64.restype = ctypes.c_int
     L.modchol_kernel_class.argtypes = [ctypes.c_int, ctypes.c_int, i32]
     L.modchol_kernel_class.restype = ctypes.c_char_p
+    L.modchol_set_small_kernel_family.argtypes = [ctypes.c_int]
+    L.modchol_set_small_kernel_family.restype = ctypes.c_int
     L.modchol_launch_count.restype = i64
     L.modchol_last_error.restype = ctypes.c_char_p
     L.modchol_version.restype = ctypes.c_int

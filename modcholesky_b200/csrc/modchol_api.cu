@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -120,13 +121,32 @@ int slot_reserve(Slot& s, size_t mats, int n)
 }
 
 // ---- size-class dispatch ---------------------------------------------------------------
-enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2 };
+enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3 };
+
+// Which small-n family serves n <= 32 (0 auto, 1 registers, 2 shared memory); initialised
+// from MODCHOL_SMALL_KERNEL=reg|wsm, changed by modchol_set_small_kernel_family().
+std::atomic<int> g_small_family{-1};
+int small_kernel_pref()
+{
+    int v = g_small_family.load();
+    if (v < 0) {
+        const char* e = getenv("MODCHOL_SMALL_KERNEL");
+        v = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'w' ? 2 : 0));
+        g_small_family.store(v);
+    }
+    return v;
+}
 
 int cta_ld(int n) { return (n & 1) ? n : n + 1; }
 
 KernelClass classify(int algo, int mode, int n, int smem_optin)
 {
-    if (warp_kernel_available(algo, mode, n))
+    const bool reg_ok = warp_kernel_available(algo, mode, n);
+    const bool wsm_ok = wsm_kernel_available(algo, mode, n);
+    const int pref = small_kernel_pref();
+    if (wsm_ok && (pref == 2 || !reg_ok))
+        return kClsWarpSmem;
+    if (reg_ok)
         return kClsWarp;
     if (smem_optin <= 0)
         smem_optin = 227 * 1024;
@@ -176,6 +196,13 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
         g_launches.fetch_add(1);
         if (ce != cudaSuccess)
             return fail(MODCHOL_ERR_CUDA, "warp kernel launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    if (cls == kClsWarpSmem) {
+        cudaError_t ce = launch_wsm_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "wsm kernel launch failed: %s", cudaGetErrorString(ce));
         return MODCHOL_OK;
     }
     const bool use_smem = cls == kClsCtaSmem;
@@ -269,12 +296,20 @@ int modchol_device_count(void) { return device_count(); }
 
 int64_t modchol_launch_count(void) { return g_launches.load(); }
 
+int modchol_set_small_kernel_family(int family)
+{
+    const int prev = small_kernel_pref();
+    g_small_family.store(family == 1 || family == 2 ? family : 0);
+    return prev;
+}
+
 const char* modchol_kernel_class(int algo, int mode, int32_t n)
 {
     if (n < 1 || n > MODCHOL_MAX_N || algo < 0 || algo > 2)
         return "unsupported";
     switch (classify(algo, mode, n, 0)) {
     case kClsWarp: return "warp32";
+    case kClsWarpSmem: return "warp_smem";
     case kClsCtaSmem: return "cta_smem";
     default: return "cta_gmem";
     }

@@ -1,0 +1,47 @@
+// wsm_inst.cu -- instantiates the shared-memory-resident warp kernels (wsm_se.cuh) for ONE
+// (algorithm, mode) pair: -DMODCHOL_INST_ALGO={1,2} -DMODCHOL_INST_STRICT={0,1}.
+#include "warp_kernels.cuh"
+#include "wsm_se.cuh"
+
+#ifndef MODCHOL_INST_ALGO
+#error "compile with -DMODCHOL_INST_ALGO=.. -DMODCHOL_INST_STRICT=.."
+#endif
+
+namespace modchol {
+
+template <int kAlgo, int R, bool kStrict>
+static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l, double* e,
+                              unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    constexpr int kWarps = 4;
+    constexpr int kMinBlocks = R == 1 ? 8 : 3;
+    auto kern = wsm_se_kernel<kAlgo, R, kStrict, kWarps, kMinBlocks>;
+    const int wstride = wsm_warp_doubles(n);
+    const size_t smem = (size_t)kWarps * wstride * sizeof(double);
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    int occ = 1;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem);
+    if (ce != cudaSuccess) return ce;
+    if (occ < 1) occ = 1;
+    long long blocks = (batch + kWarps - 1) / kWarps;
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
+    kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(n, wstride, batch, a, l, e, p, k);
+    return cudaGetLastError();
+}
+
+#define MODCHOL_CAT2(a, b, c, d) a##b##c##d
+#define MODCHOL_CAT(a, b, c, d) MODCHOL_CAT2(a, b, c, d)
+cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT)(
+    int n, long long batch, const double* a, double* l, double* e, unsigned long long* p, int* k,
+    int sms, cudaStream_t st)
+{
+    constexpr int A = MODCHOL_INST_ALGO;
+    constexpr bool S = MODCHOL_INST_STRICT != 0;
+    if (n <= 32)
+        return launch_wsm<A, 1, S>(n, batch, a, l, e, p, k, sms, st);
+    return launch_wsm<A, 2, S>(n, batch, a, l, e, p, k, sms, st);
+}
+
+}  // namespace modchol

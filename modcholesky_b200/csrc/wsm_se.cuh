@@ -1,0 +1,475 @@
+// wsm_se.cuh -- SE90 / SE99 with the matrix resident in SHARED memory: one warp per matrix,
+// packed lower triangle, lane = permuted position (row), R rows per lane (n <= 32 R).
+//
+// Why a second small-n family next to the register-resident kernels (warp_se.cuh):
+//   * the register kernels keep full rows (the symmetric half is redundant) and the 32x32
+//     matrix takes 64 of ~124 registers, which caps an SM at 16 matrices in flight; every warp
+//     is latency bound on its own dependent chain (profiles/r01_notes.md).  Here a matrix costs
+//     n(n+1)/2 doubles of shared memory (4.2 KB at n = 32, 16.6 KB at n = 64) and ~50
+//     registers per lane, so 3x more matrices are in flight per SM.
+//   * rows live at their permuted POSITION, so the symmetric row/column swap
+//     (utils.rs:30-49) is four shared-memory accesses per lane, all indexing is run-time
+//     (no per-j code specialisation, 10x less SASS), and only the lower triangle is updated.
+//   * packed row-major lower storage, element (i,k) at T(i)+k with T(i) = i(i+1)/2: the
+//     triangular numbers are a permutation modulo 16 on every aligned run of 16 rows, so a
+//     column access by 32 lanes (8-byte elements, 16 lanes per wavefront) is conflict free.
+// Only the lower triangle of A is read (A symmetric), so DRAM reads drop below the
+// algorithmic 8 n^2 bytes.
+#pragma once
+#include "warp_common.cuh"
+
+namespace modchol {
+
+__host__ __device__ constexpr int tri(int i) { return (i * (i + 1)) >> 1; }
+
+// doubles of shared memory per warp: packed triangle + 16 scratch + a 64-entry column line,
+// kept 16-byte aligned
+__host__ __device__ inline int wsm_warp_doubles(int n) { return ((tri(n) + 1) & ~1) + 16 + 72; }
+
+// local (per lane, over its R rows) then warp-wide extreme of v over candidate rows.
+template <bool kMax, int R>
+__device__ __forceinline__ double wsm_extreme(const double (&v)[R], const bool (&cand)[R], double none,
+                                              bool (&win)[R])
+{
+    int khi[R];
+    unsigned klo[R];
+    bool c[R];
+    int bh = (int)0x80000000;
+    unsigned bl = 0u;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        make_key(v[s], khi[s], klo[s]);
+        c[s] = cand[s] && (v[s] == v[s]);
+        if (!kMax) {
+            khi[s] = ~khi[s];
+            klo[s] = ~klo[s];
+        }
+        if (c[s] && (khi[s] > bh || (khi[s] == bh && klo[s] > bl))) {
+            bh = khi[s];
+            bl = klo[s];
+        }
+    }
+    const int INT_MIN_ = (int)0x80000000;
+    const int mh = __reduce_max_sync(kFull, bh);
+    const unsigned ml = __reduce_max_sync(kFull, bh == mh ? bl : 0u);
+#pragma unroll
+    for (int s = 0; s < R; ++s)
+        win[s] = c[s] && khi[s] == mh && klo[s] == ml;
+    if (mh == INT_MIN_)
+        return none;
+    return kMax ? key_value(mh, ml) : key_value(~mh, ~ml);
+}
+
+// first-strict-maximum pivot search over rows [lo, n) (utils.rs:52-91): position of the winner
+template <int R>
+__device__ __forceinline__ int wsm_argmax_first(const double (&v)[R], const bool (&active)[R],
+                                                const int (&row)[R], int lo, double& best)
+{
+    bool win[R];
+    best = wsm_extreme<true, R>(v, active, -INFINITY, win);
+    unsigned mine = 1024u;
+    bool head_nan = false;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        if (win[s] && (unsigned)row[s] < mine)
+            mine = (unsigned)row[s];
+        head_nan = head_nan || (active[s] && row[s] == lo && (v[s] != v[s]));
+    }
+    int m = (int)__reduce_min_sync(kFull, mine);
+    if (__any_sync(kFull, head_nan) || m > 255)
+        m = lo;
+    return m;
+}
+
+// ndarray-order sum of |W(lo + t, col)|, t = 0 .. len-1 (a column below the diagonal), any len:
+// lanes 0..7 own the eight partials, then ((0+(p0+p4))+(p1+p5))+(p2+p6))+(p3+p7), then the tail.
+__device__ __forceinline__ double wsm_nd_sum_abs_col(const double* W, int lo, int col, int len, int lane)
+{
+    const int nch = len >> 3;
+    double p = 0.0;
+    if (lane < 8)
+        for (int c = 0; c < nch; ++c) {
+            const int r = lo + 8 * c + lane;
+            p = dadd(p, fabs(W[tri(r) + col]));
+        }
+    const double pair = dadd(p, __shfl_down_sync(kFull, p, 4));
+    double acc = dadd(0.0, __shfl_sync(kFull, pair, 0));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 1));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 2));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 3));
+    for (int i = 8 * nch; i < len; ++i) {
+        const int r = lo + i;
+        acc = dadd(acc, fabs(W[tri(r) + col]));
+    }
+    return acc;
+}
+
+// ndarray-order sum of |x[0 .. len)| with element t at W[base(t)], executed by ONE lane.
+template <typename AddrFn>
+__device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, AddrFn addr)
+{
+    double p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        p[u] = 0.0;
+    int t = 0;
+    for (; t + 8 <= len; t += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            p[u] = dadd(p[u], fabs(W[addr(t + u)]));
+    }
+    double acc = 0.0;
+    acc = dadd(acc, dadd(p[0], p[4]));
+    acc = dadd(acc, dadd(p[1], p[5]));
+    acc = dadd(acc, dadd(p[2], p[6]));
+    acc = dadd(acc, dadd(p[3], p[7]));
+    for (; t < len; ++t)
+        acc = dadd(acc, fabs(W[addr(t)]));
+    return acc;
+}
+
+template <int kAlgo, int R, bool kStrict, int kWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
+wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
+              double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
+              int* __restrict__ K)
+{
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* W = sm + (size_t)wib * wstride;
+    double* scr = W + ((tri(n) + 1) & ~1);
+    double* line = scr + 16;   // scaled pivot column by position (broadcast source)
+    const size_t nn = (size_t)n * n;
+    const long long nwarps = (long long)gridDim.x * kWarps;
+
+    int row[R], ti[R];
+    bool rv[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        row[s] = lane + 32 * s;
+        ti[s] = tri(row[s]);
+        rv[s] = row[s] < n;
+    }
+
+    for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nwarps) {
+        const double* Ab = A + (size_t)b * nn;
+        // ---- load the lower triangle, row by row (coalesced) -----------------------------
+        __syncwarp();
+        for (int i = 0; i < n; ++i)
+            for (int k = lane; k <= i; k += 32)
+                W[tri(i) + k] = __ldg(Ab + (size_t)i * n + k);
+        __syncwarp();
+
+        double dg[R], g[R], ev[R];
+        int perm[R];
+        double av[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            dg[s] = rv[s] ? W[ti[s] + row[s]] : 0.0;
+            g[s] = 0.0;
+            ev[s] = 0.0;
+            perm[s] = row[s];
+            av[s] = fabs(dg[s]);
+        }
+        bool win[R];
+        // gamma = max |a_ii| folded from 0.0 (se90.rs:55-57, se99.rs:54-56)
+        const double gamma = wsm_extreme<true, R>(av, rv, 0.0, win);
+        const double taugamma = dmul(MODCHOL_TAU, gamma);
+        double delta_prev = 0.0;
+        int kstart = -1;
+
+        // symmetric exchange of positions j < m in the packed lower triangle + row scalars
+        auto swap_positions = [&](int j, int m, bool with_g) {
+            const int tj = tri(j), tm = tri(m);
+            int a1[R], a2[R];
+            double t1[R], t2[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const int i = row[s];
+                a1[s] = -1;
+                a2[s] = 0;
+                if (rv[s]) {
+                    if (i < j) {
+                        a1[s] = tj + i;   // (j,i) <-> (m,i)
+                        a2[s] = tm + i;
+                    } else if (i == j) {
+                        a1[s] = tj + j;   // diagonals
+                        a2[s] = tm + m;
+                    } else if (i < m) {
+                        a1[s] = ti[s] + j;   // (i,j) <-> (m,i)
+                        a2[s] = tm + i;
+                    } else if (i > m) {
+                        a1[s] = ti[s] + j;   // (i,j) <-> (i,m)
+                        a2[s] = ti[s] + m;
+                    }
+                }
+                if (a1[s] >= 0) {
+                    t1[s] = W[a1[s]];
+                    t2[s] = W[a2[s]];
+                }
+                // row scalars of positions j and m travel through the scratch line
+                if (i == j || i == m) {
+                    double* q = scr + (i == j ? 0 : 4);
+                    q[0] = dg[s];
+                    q[1] = g[s];
+                    q[2] = (double)perm[s];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const int i = row[s];
+                if (a1[s] >= 0) {
+                    W[a1[s]] = t2[s];
+                    W[a2[s]] = t1[s];
+                }
+                if (i == j || i == m) {
+                    const double* q = scr + (i == j ? 4 : 0);
+                    dg[s] = q[0];
+                    if (with_g)
+                        g[s] = q[1];
+                    perm[s] = (int)q[2];
+                }
+            }
+            __syncwarp();
+        };
+        // value v[s] of the row at position j, broadcast to the warp
+        auto bcast_row = [&](const double (&v)[R], int j) -> double {
+            double x = v[0];
+#pragma unroll
+            for (int s = 1; s < R; ++s)
+                if ((j >> 5) == s)
+                    x = v[s];
+            return __shfl_sync(kFull, x, j & 31);
+        };
+        // D: s = sqrt(pivot), y such that cs = col*y (FAST) -- see warp_se.cuh
+        auto scale = [&](double piv, double& sq, double& y, double& inv_piv) -> bool {
+            const bool fast = !kStrict && fast_range_ok(piv);
+            if (fast) {
+                y = rsqrt_normal(piv);
+                sq = dmul(piv, y);
+                inv_piv = dmul(y, y);
+            } else {
+                sq = dsqrt(piv);
+                y = 0.0;
+                inv_piv = 0.0;
+            }
+            return fast;
+        };
+        // E: write column j of L and update the trailing lower triangle
+        // (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171)
+        auto eliminate = [&](int j, double sq, const double (&cs)[R], const double (&dg_new)[R]) {
+            const int tj = tri(j);
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                if (rv[s])
+                    line[row[s]] = cs[s];
+                if (rv[s] && row[s] > j) {
+                    W[ti[s] + j] = cs[s];
+                    dg[s] = dg_new[s];
+                } else if (row[s] == j) {
+                    W[tj + j] = sq;
+                }
+            }
+            __syncwarp();
+            // W(i,k) -= cs_i * cs_k for j < k <= i.  Four columns per trip; the first trip is
+            // aligned down to an even k so that the broadcast reads are LDS.128.
+            const int k0 = (j + 1) & ~1;
+            for (int k = k0; k < n; k += 4) {
+                const double2 c01 = *reinterpret_cast<const double2*>(&line[k]);
+                const double2 c23 = *reinterpret_cast<const double2*>(&line[k + 2]);
+                const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    double* wr = W + ti[s] + k;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (rv[s] && k + u > j && k + u <= row[s])
+                            wr[u] = nmul_add<kStrict>(wr[u], cs[s], ck[u]);
+                }
+            }
+            __syncwarp();
+        };
+
+        // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
+        int j = 0;
+        for (; j < n; ++j) {
+            bool active[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s)
+                active[s] = rv[s] && row[s] >= j;
+            double dmax;
+            const int m = wsm_argmax_first<R>(dg, active, row, j, dmax);
+            if (kAlgo == kSE99) {  // se99.rs:62-73, before the pivot is applied
+                const double dmin = wsm_extreme<false, R>(dg, active, INFINITY, win);
+                if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
+                    kstart = j;
+                    break;
+                }
+            }
+            if (m != j)
+                swap_positions(j, m, false);
+            const double piv = bcast_row(dg, j);
+            double sq, y, inv_piv;
+            const bool fast = scale(piv, sq, y, inv_piv);
+            double cs[R], dg_new[R], nv[R];
+            bool below[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                below[s] = rv[s] && row[s] > j;
+                const double col = below[s] ? W[ti[s] + j] : 0.0;
+                cs[s] = fast ? dmul(col, y) : ddiv(col, sq);
+                dg_new[s] = nmul_add<kStrict>(dg[s], cs[s], cs[s]);
+                // look-ahead value (se90.rs:70-77, se99.rs:82-89); FAST: the updated diagonal
+                nv[s] = fast ? dg_new[s] : dsub(dg[s], ddiv(dmul(col, col), piv));
+            }
+            const double la = wsm_extreme<false, R>(nv, below, INFINITY, win);
+            const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
+            if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
+                kstart = j;
+                break;
+            }
+            eliminate(j, sq, cs, dg_new);
+        }
+
+        // ---- phase 2 ----------------------------------------------------------------------
+        if (kstart >= 0) {
+            if (kAlgo == kSE99 && kstart == n - 1) {  // se99.rs:115-119
+                const double ljj = bcast_row(dg, n - 1);
+                const double ej = tail1x1_e(ljj, gamma);
+#pragma unroll
+                for (int s = 0; s < R; ++s)
+                    if (row[s] == n - 1) {
+                        ev[s] = ej;
+                        W[ti[s] + row[s]] = dsqrt(dadd(ljj, ej));
+                    }
+            } else {
+                // lower Gershgorin bounds (se90.rs:105-110, se99.rs:125-130)
+                const int k0 = kstart;
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = row[s];
+                    if (rv[s] && i >= k0) {
+                        double s1, s2;
+                        if constexpr (kStrict) {
+                            s1 = wsm_nd_sum_abs_lane(W, i - k0, [&](int t) { return ti[s] + k0 + t; });
+                            s2 = wsm_nd_sum_abs_lane(W, n - 1 - i, [&](int t) { return tri(i + 1 + t) + i; });
+                            g[s] = dsub(dsub(dg[s], s1), s2);
+                        } else {
+                            s1 = 0.0;
+                            s2 = 0.0;
+                            for (int c = k0; c < i; ++c)
+                                s1 = dadd(s1, fabs(W[ti[s] + c]));
+                            int tr = tri(i + 1) + i;
+                            for (int r = i + 1; r < n; ++r) {
+                                s2 = dadd(s2, fabs(W[tr]));
+                                tr += r + 1;
+                            }
+                            g[s] = dsub(dg[s], dadd(s1, s2));
+                        }
+                    }
+                }
+                for (j = k0; j + 2 < n; ++j) {
+                    bool active[R];
+#pragma unroll
+                    for (int s = 0; s < R; ++s)
+                        active[s] = rv[s] && row[s] >= j;
+                    double gmax;  // se90.rs:115, se99.rs:135
+                    const int m = wsm_argmax_first<R>(g, active, row, j, gmax);
+                    if (m != j)
+                        swap_positions(j, m, true);
+                    double piv = bcast_row(dg, j);
+                    double col[R], acol[R];
+                    bool below[R];
+                    double part = 0.0;
+#pragma unroll
+                    for (int s = 0; s < R; ++s) {
+                        below[s] = rv[s] && row[s] > j;
+                        col[s] = below[s] ? W[ti[s] + j] : 0.0;
+                        acol[s] = abs_bits(col[s]);
+                        part = dadd(part, acol[s]);
+                    }
+                    // E_jj (se90.rs:124-131, se99.rs:144-151)
+                    double normj;
+                    if constexpr (kStrict)
+                        normj = wsm_nd_sum_abs_col(W, j + 1, j, n - j - 1, lane);
+                    else
+                        normj = warp_sum_tree<32>(kFull, part);
+                    const double ej =
+                        max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
+                    if (kStrict) {
+                        if (ej > 0.0) {
+                            piv = dadd(piv, ej);
+                            delta_prev = ej;
+                        }
+                    } else {
+                        piv = dadd(piv, ej);
+                        delta_prev = ej;
+                    }
+                    double sq, y, inv_piv;
+                    const bool fast = scale(piv, sq, y, inv_piv);
+                    // bound update (se90.rs:134-139, se99.rs:154-159)
+                    const bool upd = fabs(dsub(piv, normj)) > MODCHOL_EPS;
+                    double t = 0.0;
+                    if (upd)
+                        t = fast ? __fma_rn(-normj, inv_piv, 1.0) : dsub(1.0, ddiv(normj, piv));
+                    double cs[R], dg_new[R];
+#pragma unroll
+                    for (int s = 0; s < R; ++s) {
+                        if (row[s] == j)
+                            ev[s] = ej;
+                        cs[s] = fast ? dmul(col[s], y) : ddiv(col[s], sq);
+                        dg_new[s] = nmul_add<kStrict>(dg[s], cs[s], cs[s]);
+                        if (upd && below[s])
+                            g[s] = mul_add<kStrict>(g[s], acol[s], t);
+                    }
+                    eliminate(j, sq, cs, dg_new);
+                }
+                // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186)
+                double a00 = bcast_row(dg, n - 2);
+                double a11 = bcast_row(dg, n - 1);
+                double a10 = W[tri(n - 1) + n - 2];
+                double lhi, llo;
+                eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);   // lower storage: m[0,1] == m[1,0]
+                const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
+                if (en > 0.0) {
+                    a00 = dadd(a00, en);
+                    a11 = dadd(a11, en);
+                }
+                a00 = dsqrt(a00);
+                a10 = ddiv(a10, a00);
+                a11 = dsqrt(dsub(a11, dmul(a10, a10)));
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    if (row[s] == n - 2) {
+                        ev[s] = en;
+                        W[ti[s] + row[s]] = a00;
+                    }
+                    if (row[s] == n - 1) {
+                        ev[s] = en;
+                        W[ti[s] + n - 2] = a10;
+                        W[ti[s] + row[s]] = a11;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- epilogue: L (strict upper explicitly zero), e un-permuted, p -------------------
+        double* Lb = L + (size_t)b * nn;
+        for (int i = 0; i < n; ++i)
+            for (int k = lane; k < n; k += 32)
+                Lb[(size_t)i * n + k] = (k <= i) ? W[tri(i) + k] : 0.0;
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            if (rv[s]) {
+                E[(size_t)b * n + perm[s]] = ev[s];                       // se99.rs:194-198
+                P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
+            }
+        if (K && lane == 0)
+            K[b] = kstart;
+    }
+}
+
+}  // namespace modchol

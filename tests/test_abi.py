@@ -37,7 +37,8 @@ def test_header_and_library_agree():
 def test_version_and_kernel_classes():
     assert m.lib().modchol_version() == 100
     assert m.kernel_class("gmw81", 256) in ("cta_gmem", "cluster")
-    assert m.kernel_class("se90", 64) in ("cta_smem", "warp64")
+    assert m.kernel_class("se90", 64) == "warp_smem"
+    assert m.kernel_class("se99", 32) == "warp32" and m.kernel_class("gmw81", 64) == "cta_smem"
     assert m.kernel_class("se99", 4096) == "unsupported"
 
 

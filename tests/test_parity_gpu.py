@@ -76,20 +76,25 @@ def _assert_tolerance(tag, a, got, ref):
 # ---- the reference's own tests, run through the mirrored trait API on the GPU -------------
 @pytest.mark.parametrize("mode", ["strict", "fast"])
 def test_reference_test_suite_on_gpu(golden, torch_cuda, mode):
+    """STRICT: the reference's assertions verbatim (absolute tolerances).  FAST: the same
+    assertions with the tolerance taken relative to max(1, max|A|) -- the reference's absolute
+    1e-12 on A4 (entries ~4.8e3) is 0.2 ulp and only its exact arithmetic can promise it; the
+    north-star bar is relative (||LL^T - P(A+E)P^T|| / ||A|| <= 1e-12)."""
     for case in golden["cases"]:
         a = np.array(golden["matrices"][case["matrix"]]["a"], dtype=np.float64)
+        scale = 1.0 if mode == "strict" else max(1.0, np.abs(a).max())
         d = getattr(m.Array2(a, mode=mode), "mod_cholesky_" + case["algo"])()
         l, e, p = d.l, d.e, d.p
-        assert identity_residual(a, l, e, p) < case["tol_identity"], case["name"]
+        assert identity_residual(a, l, e, p) < case["tol_identity"] * scale, case["name"]
         llt = l @ l.T
         if "u" in case:
             u = np.array(case["u"])
-            assert np.abs(llt - u.T @ u).max() < case["tol_llt"], case["name"]
+            assert np.abs(llt - u.T @ u).max() < case["tol_llt"] * scale, case["name"]
         if "res" in case:
             P = perm_matrix(p)
-            assert np.abs(llt - P @ np.array(case["res"]) @ P.T).max() < case["tol_llt"], case["name"]
+            assert np.abs(llt - P @ np.array(case["res"]) @ P.T).max() < case["tol_llt"] * scale, case["name"]
         if "l" in case:
-            assert np.abs(l - np.array(case["l"])).max() < case["tol_l"], case["name"]
+            assert np.abs(l - np.array(case["l"])).max() < case["tol_l"] * scale, case["name"]
 
 
 def test_gershgorin_circles_on_gpu(golden, oracle, torch_cuda):
@@ -117,6 +122,26 @@ def test_strict_bit_exact_vs_oracle(oracle, torch_cuda, algo, n):
         a = matgen.make(fam, 1000 + n, b, n)
         ref = oracle.factor_batched(algo, a)
         _assert_bit_exact(f"{algo} n={n} {fam}", _gpu(torch_cuda, algo, a, "strict"), ref)
+
+
+@pytest.mark.parametrize("family", ["reg", "wsm"])
+def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
+    """n <= 32 is served by the register-resident kernels by default; the shared-memory-resident
+    family (default for 32 < n <= 64) must give the same bits there too."""
+    prev = m.set_small_kernel_family(family)
+    try:
+        for algo in ("se90", "se99"):
+            for n in (1, 2, 5, 8, 16, 17, 31, 32):
+                assert m.kernel_class(algo, n) == ("warp32" if family == "reg" else "warp_smem")
+                for fam in ("uniform", "wishart", "ties"):
+                    a = matgen.make(fam, 4000 + n, 64, n)
+                    ref = oracle.factor_batched(algo, a)
+                    _assert_bit_exact(f"{family} {algo} n={n} {fam}", _gpu(torch_cuda, algo, a, "strict"), ref)
+                    if fam != "ties" and n >= 3:   # exact ties are covered by the tie test
+                        _assert_tolerance(f"{family} {algo} n={n} {fam}", a,
+                                          _gpu(torch_cuda, algo, a, "fast"), ref)
+    finally:
+        m.set_small_kernel_family(prev)
 
 
 @pytest.mark.parametrize("algo", ALGOS)
