@@ -22,6 +22,15 @@ namespace modchol {
 
 __host__ __device__ constexpr int tri(int i) { return (i * (i + 1)) >> 1; }
 
+// st.shared.f64 [p], v  executed only where pred -- as ONE predicated instruction (written as
+// `if (pred) *p = v;` the compiler wraps every element update in a BSSY/BRA/BSYNC diamond).
+__device__ __forceinline__ void st_shared_if(bool pred, double* p, double v)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}"
+                 :: "r"(a), "d"(v), "r"((int)pred) : "memory");
+}
+
 // doubles of shared memory per warp: packed triangle + 16 scratch + a 64-entry column line,
 // kept 16-byte aligned
 __host__ __device__ inline int wsm_warp_doubles(int n) { return ((tri(n) + 1) & ~1) + 16 + 72; }
@@ -153,11 +162,26 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
 
     for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nwarps) {
         const double* Ab = A + (size_t)b * nn;
-        // ---- load the lower triangle, row by row (coalesced) -----------------------------
+        // ---- load the lower triangle, eight rows per trip (coalesced, loads batched) --------
         __syncwarp();
-        for (int i = 0; i < n; ++i)
-            for (int k = lane; k <= i; k += 32)
-                W[tri(i) + k] = __ldg(Ab + (size_t)i * n + k);
+        for (int i0 = 0; i0 < n; i0 += 8) {
+            double v[8][R];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = i0 + u, k = lane + 32 * s;
+                    v[u][s] = (i < n && k <= i) ? __ldg(Ab + i * n + k) : 0.0;
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = i0 + u, k = lane + 32 * s;
+                    if (i < n && k <= i)
+                        W[tri(i) + k] = v[u][s];
+                }
+        }
         __syncwarp();
 
         double dg[R], g[R], ev[R];
@@ -273,19 +297,31 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             }
             __syncwarp();
             // W(i,k) -= cs_i * cs_k for j < k <= i.  Four columns per trip; the first trip is
-            // aligned down to an even k so that the broadcast reads are LDS.128.
+            // aligned down to an even k so that the broadcast reads are LDS.128.  Loads and
+            // FMAs are unconditional (a lane may read past the end of its own row: still inside
+            // this warp's region); only the store is predicated on j < k <= row.
             const int k0 = (j + 1) & ~1;
+            unsigned cnt[R];
+            double* wr[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const int c = rv[s] ? row[s] - j : 0;
+                cnt[s] = c > 0 ? (unsigned)c : 0u;          // columns j+1 .. row[s]
+                wr[s] = W + (rv[s] ? ti[s] : 0) + k0;
+            }
             for (int k = k0; k < n; k += 4) {
                 const double2 c01 = *reinterpret_cast<const double2*>(&line[k]);
                 const double2 c23 = *reinterpret_cast<const double2*>(&line[k + 2]);
                 const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
+                const unsigned off = (unsigned)(k - j - 1);  // wraps to UINT_MAX for k == j
 #pragma unroll
                 for (int s = 0; s < R; ++s) {
-                    double* wr = W + ti[s] + k;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (rv[s] && k + u > j && k + u <= row[s])
-                            wr[u] = nmul_add<kStrict>(wr[u], cs[s], ck[u]);
+                    for (int u = 0; u < 4; ++u) {
+                        const double v = nmul_add<kStrict>(wr[s][u], cs[s], ck[u]);
+                        st_shared_if(off + (unsigned)u < cnt[s], wr[s] + u, v);
+                    }
+                    wr[s] += 4;
                 }
             }
             __syncwarp();
@@ -458,9 +494,16 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
 
         // ---- epilogue: L (strict upper explicitly zero), e un-permuted, p -------------------
         double* Lb = L + (size_t)b * nn;
-        for (int i = 0; i < n; ++i)
-            for (int k = lane; k < n; k += 32)
-                Lb[(size_t)i * n + k] = (k <= i) ? W[tri(i) + k] : 0.0;
+        for (int i0 = 0; i0 < n; i0 += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = i0 + u, k = lane + 32 * s;
+                    if (i < n && k < n)
+                        Lb[i * n + k] = (k <= i) ? W[tri(i) + k] : 0.0;
+                }
+        }
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if (rv[s]) {
