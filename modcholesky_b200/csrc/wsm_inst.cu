@@ -3,6 +3,9 @@
 #include "warp_kernels.cuh"
 #include "wsm_se.cuh"
 
+#ifndef MODCHOL_WSM_MINB
+#define MODCHOL_WSM_MINB 6   /* resident 4-warp blocks per SM asked of ptxas for n <= 32 */
+#endif
 #ifndef MODCHOL_INST_ALGO
 #error "compile with -DMODCHOL_INST_ALGO=.. -DMODCHOL_INST_STRICT=.."
 #endif
@@ -14,7 +17,7 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
     constexpr int kWarps = 4;
-    constexpr int kMinBlocks = R == 1 ? 8 : 3;
+    constexpr int kMinBlocks = R == 1 ? MODCHOL_WSM_MINB : 3;
     auto kern = wsm_se_kernel<kAlgo, R, kStrict, kWarps, kMinBlocks>;
     const int wstride = wsm_warp_doubles(n);
     const size_t smem = (size_t)kWarps * wstride * sizeof(double);
