@@ -90,6 +90,31 @@ __device__ __forceinline__ int wsm_argmax_first(const double (&v)[R], const bool
     return m;
 }
 
+// Explicit 32-bit shared-window addressing.  With generic `double*` accesses the compiler keeps
+// re-deriving the shared window base (S2R / S2UR / ULEA) under register pressure; one `unsigned`
+// byte address per warp plus these accessors removes ~60 instructions per step.
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f64_if(bool pred, unsigned a, double v)
+{
+    asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}"
+                 :: "r"(a), "d"(v), "r"((int)pred) : "memory");
+}
+
 // ndarray-order sum of |W(lo + t, col)|, t = 0 .. len-1 (a column below the diagonal), any len:
 // lanes 0..7 own the eight partials, then ((0+(p0+p4))+(p1+p5))+(p2+p6))+(p3+p7), then the tail.
 __device__ __forceinline__ double wsm_nd_sum_abs_col(const double* W, int lo, int col, int len, int lane)
@@ -146,18 +171,20 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* W = sm + (size_t)wib * wstride;
-    double* scr = W + ((tri(n) + 1) & ~1);
-    double* line = scr + 16;   // scaled pivot column by position (broadcast source)
+    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);          // byte address of W(0,0)
+    const unsigned scrb = wb + 8u * (unsigned)((tri(n) + 1) & ~1);      // 16 doubles of scratch
+    const unsigned lineb = scrb + 128u;                                  // 72-entry column line
     const size_t nn = (size_t)n * n;
     const long long nwarps = (long long)gridDim.x * kWarps;
 
-    int row[R], ti[R];
+    int row[R];
+    unsigned tib[R];   // byte address of W(row, 0)
     bool rv[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
         row[s] = lane + 32 * s;
-        ti[s] = tri(row[s]);
         rv[s] = row[s] < n;
+        tib[s] = wb + 8u * (unsigned)tri(rv[s] ? row[s] : 0);
     }
 
     for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nwarps) {
@@ -178,8 +205,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
 #pragma unroll
                 for (int s = 0; s < R; ++s) {
                     const int i = i0 + u, k = lane + 32 * s;
-                    if (i < n && k <= i)
-                        W[tri(i) + k] = v[u][s];
+                    sts_f64_if(i < n && k <= i, wb + 8u * (unsigned)(tri(i) + k), v[u][s]);
                 }
         }
         __syncwarp();
@@ -189,7 +215,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         double av[R];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            dg[s] = rv[s] ? W[ti[s] + row[s]] : 0.0;
+            dg[s] = rv[s] ? lds_f64(tib[s] + 8u * row[s]) : 0.0;
             g[s] = 0.0;
             ev[s] = 0.0;
             perm[s] = row[s];
@@ -202,57 +228,62 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         double delta_prev = 0.0;
         int kstart = -1;
 
-        // symmetric exchange of positions j < m in the packed lower triangle + row scalars
-        auto swap_positions = [&](int j, int m, bool with_g) {
-            const int tj = tri(j), tm = tri(m);
-            int a1[R], a2[R];
+        // symmetric exchange of positions j < m in the packed lower triangle (utils.rs:30-49):
+        //   i < j     : (j,i) <-> (m,i)        i == j : (j,j) <-> (m,m)
+        //   j < i < m : (i,j) <-> (m,i)        i == m : (m,j) stays        i > m : (i,j) <-> (i,m)
+        // tjb = byte address of W(j,0).  Branch free: two address selects, two loads, two
+        // predicated stores per row; the row scalars of positions j and m are exchanged by
+        // shuffle (R == 1) or through the scratch line (R == 2).
+        auto swap_positions = [&](int j, int m, unsigned tjb, bool with_g) {
+            const unsigned tmb = wb + 8u * (unsigned)tri(m);
+            unsigned a1[R], a2[R];
             double t1[R], t2[R];
+            bool act[R];
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 const int i = row[s];
-                a1[s] = -1;
-                a2[s] = 0;
-                if (rv[s]) {
-                    if (i < j) {
-                        a1[s] = tj + i;   // (j,i) <-> (m,i)
-                        a2[s] = tm + i;
-                    } else if (i == j) {
-                        a1[s] = tj + j;   // diagonals
-                        a2[s] = tm + m;
-                    } else if (i < m) {
-                        a1[s] = ti[s] + j;   // (i,j) <-> (m,i)
-                        a2[s] = tm + i;
-                    } else if (i > m) {
-                        a1[s] = ti[s] + j;   // (i,j) <-> (i,m)
-                        a2[s] = ti[s] + m;
+                act[s] = rv[s] && i != m;
+                a1[s] = (i <= j) ? tjb + 8u * i : tib[s] + 8u * j;
+                a2[s] = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib[s] + 8u * m);
+                if (!act[s]) {
+                    a1[s] = wb;
+                    a2[s] = wb;
+                }
+                t1[s] = lds_f64(a1[s]);
+                t2[s] = lds_f64(a2[s]);
+            }
+            if constexpr (R == 1) {
+                const int partner = (lane == j) ? m : ((lane == m) ? j : lane);
+                dg[0] = __shfl_sync(kFull, dg[0], partner);
+                if (with_g)
+                    g[0] = __shfl_sync(kFull, g[0], partner);
+                perm[0] = __shfl_sync(kFull, perm[0], partner);
+            } else {
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = row[s];
+                    if (i == j || i == m) {
+                        const unsigned q = scrb + (i == j ? 0u : 32u);
+                        sts_f64(q, dg[s]);
+                        sts_f64(q + 8, g[s]);
+                        sts_f64(q + 16, (double)perm[s]);
                     }
-                }
-                if (a1[s] >= 0) {
-                    t1[s] = W[a1[s]];
-                    t2[s] = W[a2[s]];
-                }
-                // row scalars of positions j and m travel through the scratch line
-                if (i == j || i == m) {
-                    double* q = scr + (i == j ? 0 : 4);
-                    q[0] = dg[s];
-                    q[1] = g[s];
-                    q[2] = (double)perm[s];
                 }
             }
             __syncwarp();
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                const int i = row[s];
-                if (a1[s] >= 0) {
-                    W[a1[s]] = t2[s];
-                    W[a2[s]] = t1[s];
-                }
-                if (i == j || i == m) {
-                    const double* q = scr + (i == j ? 4 : 0);
-                    dg[s] = q[0];
-                    if (with_g)
-                        g[s] = q[1];
-                    perm[s] = (int)q[2];
+                sts_f64_if(act[s], a1[s], t2[s]);
+                sts_f64_if(act[s], a2[s], t1[s]);
+                if constexpr (R > 1) {
+                    const int i = row[s];
+                    if (i == j || i == m) {
+                        const unsigned q = scrb + (i == j ? 32u : 0u);
+                        dg[s] = lds_f64(q);
+                        if (with_g)
+                            g[s] = lds_f64(q + 8);
+                        perm[s] = (int)lds_f64(q + 16);
+                    }
                 }
             }
             __syncwarp();
@@ -282,18 +313,16 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         };
         // E: write column j of L and update the trailing lower triangle
         // (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171)
-        auto eliminate = [&](int j, double sq, const double (&cs)[R], const double (&dg_new)[R]) {
-            const int tj = tri(j);
+        auto eliminate = [&](int j, unsigned tjb, double sq, const double (&cs)[R],
+                             const double (&dg_new)[R]) {
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                if (rv[s])
-                    line[row[s]] = cs[s];
-                if (rv[s] && row[s] > j) {
-                    W[ti[s] + j] = cs[s];
+                const bool below = rv[s] && row[s] > j;
+                sts_f64_if(rv[s], lineb + 8u * row[s], cs[s]);
+                sts_f64_if(below || row[s] == j, below ? tib[s] + 8u * j : tjb + 8u * j,
+                           below ? cs[s] : sq);
+                if (below)
                     dg[s] = dg_new[s];
-                } else if (row[s] == j) {
-                    W[tj + j] = sq;
-                }
             }
             __syncwarp();
             // W(i,k) -= cs_i * cs_k for j < k <= i.  Four columns per trip; the first trip is
@@ -301,35 +330,40 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             // FMAs are unconditional (a lane may read past the end of its own row: still inside
             // this warp's region); only the store is predicated on j < k <= row.
             const int k0 = (j + 1) & ~1;
-            unsigned cnt[R];
-            double* wr[R];
+            unsigned cnt[R], wr[R];
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 const int c = rv[s] ? row[s] - j : 0;
                 cnt[s] = c > 0 ? (unsigned)c : 0u;          // columns j+1 .. row[s]
-                wr[s] = W + (rv[s] ? ti[s] : 0) + k0;
+                wr[s] = tib[s] + 8u * k0;
             }
+            unsigned lk = lineb + 8u * k0;
             for (int k = k0; k < n; k += 4) {
-                const double2 c01 = *reinterpret_cast<const double2*>(&line[k]);
-                const double2 c23 = *reinterpret_cast<const double2*>(&line[k + 2]);
+                const double2 c01 = lds_v2f64(lk);
+                const double2 c23 = lds_v2f64(lk + 16);
                 const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
                 const unsigned off = (unsigned)(k - j - 1);  // wraps to UINT_MAX for k == j
 #pragma unroll
                 for (int s = 0; s < R; ++s) {
+                    double w[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const double v = nmul_add<kStrict>(wr[s][u], cs[s], ck[u]);
-                        st_shared_if(off + (unsigned)u < cnt[s], wr[s] + u, v);
-                    }
-                    wr[s] += 4;
+                    for (int u = 0; u < 4; ++u)
+                        w[u] = lds_f64(wr[s] + 8u * u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        sts_f64_if(off + (unsigned)u < cnt[s], wr[s] + 8u * u,
+                                   nmul_add<kStrict>(w[u], cs[s], ck[u]));
+                    wr[s] += 32;
                 }
+                lk += 32;
             }
             __syncwarp();
         };
 
         // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
         int j = 0;
-        for (; j < n; ++j) {
+        unsigned tjb = wb;   // byte address of W(j,0), advanced with j
+        for (; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
             bool active[R];
 #pragma unroll
             for (int s = 0; s < R; ++s)
@@ -344,7 +378,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 }
             }
             if (m != j)
-                swap_positions(j, m, false);
+                swap_positions(j, m, tjb, false);
             const double piv = bcast_row(dg, j);
             double sq, y, inv_piv;
             const bool fast = scale(piv, sq, y, inv_piv);
@@ -353,7 +387,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 below[s] = rv[s] && row[s] > j;
-                const double col = below[s] ? W[ti[s] + j] : 0.0;
+                const double col = below[s] ? lds_f64(tib[s] + 8u * j) : 0.0;
                 cs[s] = fast ? dmul(col, y) : ddiv(col, sq);
                 dg_new[s] = nmul_add<kStrict>(dg[s], cs[s], cs[s]);
                 // look-ahead value (se90.rs:70-77, se99.rs:82-89); FAST: the updated diagonal
@@ -365,7 +399,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 kstart = j;
                 break;
             }
-            eliminate(j, sq, cs, dg_new);
+            eliminate(j, tjb, sq, cs, dg_new);
         }
 
         // ---- phase 2 ----------------------------------------------------------------------
@@ -377,7 +411,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 for (int s = 0; s < R; ++s)
                     if (row[s] == n - 1) {
                         ev[s] = ej;
-                        W[ti[s] + row[s]] = dsqrt(dadd(ljj, ej));
+                        sts_f64(tib[s] + 8u * row[s], dsqrt(dadd(ljj, ej)));
                     }
             } else {
                 // lower Gershgorin bounds (se90.rs:105-110, se99.rs:125-130)
@@ -387,25 +421,26 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                     const int i = row[s];
                     if (rv[s] && i >= k0) {
                         double s1, s2;
+                        const int tis = (int)((tib[s] - wb) >> 3);
                         if constexpr (kStrict) {
-                            s1 = wsm_nd_sum_abs_lane(W, i - k0, [&](int t) { return ti[s] + k0 + t; });
+                            s1 = wsm_nd_sum_abs_lane(W, i - k0, [&](int t) { return tis + k0 + t; });
                             s2 = wsm_nd_sum_abs_lane(W, n - 1 - i, [&](int t) { return tri(i + 1 + t) + i; });
                             g[s] = dsub(dsub(dg[s], s1), s2);
                         } else {
                             s1 = 0.0;
                             s2 = 0.0;
                             for (int c = k0; c < i; ++c)
-                                s1 = dadd(s1, fabs(W[ti[s] + c]));
-                            int tr = tri(i + 1) + i;
+                                s1 = dadd(s1, fabs(lds_f64(tib[s] + 8u * c)));
+                            unsigned tr = wb + 8u * (unsigned)(tri(i + 1) + i);
                             for (int r = i + 1; r < n; ++r) {
-                                s2 = dadd(s2, fabs(W[tr]));
-                                tr += r + 1;
+                                s2 = dadd(s2, fabs(lds_f64(tr)));
+                                tr += 8u * (unsigned)(r + 1);
                             }
                             g[s] = dsub(dg[s], dadd(s1, s2));
                         }
                     }
                 }
-                for (j = k0; j + 2 < n; ++j) {
+                for (j = k0; j + 2 < n; tjb += 8u * (unsigned)(j + 1), ++j) {
                     bool active[R];
 #pragma unroll
                     for (int s = 0; s < R; ++s)
@@ -413,7 +448,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                     double gmax;  // se90.rs:115, se99.rs:135
                     const int m = wsm_argmax_first<R>(g, active, row, j, gmax);
                     if (m != j)
-                        swap_positions(j, m, true);
+                        swap_positions(j, m, tjb, true);
                     double piv = bcast_row(dg, j);
                     double col[R], acol[R];
                     bool below[R];
@@ -421,9 +456,9 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
 #pragma unroll
                     for (int s = 0; s < R; ++s) {
                         below[s] = rv[s] && row[s] > j;
-                        col[s] = below[s] ? W[ti[s] + j] : 0.0;
+                        col[s] = below[s] ? lds_f64(tib[s] + 8u * j) : 0.0;
                         acol[s] = abs_bits(col[s]);
-                        part = dadd(part, acol[s]);
+                        part = (s == 0) ? acol[s] : dadd(part, acol[s]);
                     }
                     // E_jj (se90.rs:124-131, se99.rs:144-151)
                     double normj;
@@ -459,12 +494,13 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                         if (upd && below[s])
                             g[s] = mul_add<kStrict>(g[s], acol[s], t);
                     }
-                    eliminate(j, sq, cs, dg_new);
+                    eliminate(j, tjb, sq, cs, dg_new);
                 }
                 // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186)
                 double a00 = bcast_row(dg, n - 2);
                 double a11 = bcast_row(dg, n - 1);
-                double a10 = W[tri(n - 1) + n - 2];
+                const unsigned a10b = wb + 8u * (unsigned)(tri(n - 1) + n - 2);
+                double a10 = lds_f64(a10b);
                 double lhi, llo;
                 eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);   // lower storage: m[0,1] == m[1,0]
                 const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
@@ -480,12 +516,12 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 for (int s = 0; s < R; ++s) {
                     if (row[s] == n - 2) {
                         ev[s] = en;
-                        W[ti[s] + row[s]] = a00;
+                        sts_f64(tib[s] + 8u * row[s], a00);
                     }
                     if (row[s] == n - 1) {
                         ev[s] = en;
-                        W[ti[s] + n - 2] = a10;
-                        W[ti[s] + row[s]] = a11;
+                        sts_f64(a10b, a10);
+                        sts_f64(tib[s] + 8u * row[s], a11);
                     }
                 }
             }
@@ -501,7 +537,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 for (int s = 0; s < R; ++s) {
                     const int i = i0 + u, k = lane + 32 * s;
                     if (i < n && k < n)
-                        Lb[i * n + k] = (k <= i) ? W[tri(i) + k] : 0.0;
+                        Lb[i * n + k] = (k <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + k)) : 0.0;
                 }
         }
 #pragma unroll
