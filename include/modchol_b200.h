@@ -114,8 +114,9 @@ int modchol_verify_batched_f64(int64_t batch, int32_t n, const double *a, const 
 const char *modchol_kernel_class(int algo, int mode, int32_t n);
 
 /* Tuning knob: which small-n kernel family serves n <= 32 for SE90/SE99 -- 0 = automatic
- * (register-resident "warp32"), 1 = register-resident, 2 = shared-memory-resident
- * ("warp_smem", always used for 32 < n <= 64).  Returns the previous setting.  Both families
+ * (register-resident "warp32" in FAST mode and for n <= 16, shared-memory-resident "warp_smem"
+ * in STRICT mode for 16 < n <= 32), 1 = register-resident, 2 = shared-memory-resident
+ * ("warp_smem" always serves 32 < n <= 64).  Returns the previous setting.  Both families
  * produce identical STRICT results; the knob exists for benchmarking and tests. */
 int modchol_set_small_kernel_family(int family);
 

@@ -4,7 +4,7 @@
 #include "wsm_se.cuh"
 
 #ifndef MODCHOL_WSM_MINB
-#define MODCHOL_WSM_MINB 6   /* resident 4-warp blocks per SM asked of ptxas for n <= 32 */
+#define MODCHOL_WSM_MINB 8   /* resident 4-warp blocks per SM asked of ptxas for n <= 32 */
 #endif
 #ifndef MODCHOL_INST_ALGO
 #error "compile with -DMODCHOL_INST_ALGO=.. -DMODCHOL_INST_STRICT=.."
@@ -22,6 +22,10 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
     const int wstride = wsm_warp_doubles(n);
     const size_t smem = (size_t)kWarps * wstride * sizeof(double);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    // the matrices live in shared memory: ask for the largest shared-memory carve-out
+    ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              (int)cudaSharedmemCarveoutMaxShared);
     if (ce != cudaSuccess) return ce;
     int occ = 1;
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem);

@@ -132,7 +132,8 @@ def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
     try:
         for algo in ("se90", "se99"):
             for n in (1, 2, 5, 8, 16, 17, 31, 32):
-                assert m.kernel_class(algo, n) == ("warp32" if family == "reg" else "warp_smem")
+                for mode in ("strict", "fast"):
+                    assert m.kernel_class(algo, n, mode) == ("warp32" if family == "reg" else "warp_smem")
                 for fam in ("uniform", "wishart", "ties"):
                     a = matgen.make(fam, 4000 + n, 64, n)
                     ref = oracle.factor_batched(algo, a)
