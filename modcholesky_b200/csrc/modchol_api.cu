@@ -148,7 +148,8 @@ KernelClass classify(int algo, int mode, int n, int smem_optin)
     // (several matrices per warp); the shared-memory family is insensitive to the input family
     // and wins in STRICT mode for 16 < n <= 32 (48 vs 22..50 M/s at n = 32) and is the only
     // warp-level kernel for 32 < n <= 64.
-    const bool auto_wsm = wsm_ok && (!reg_ok || (mode == MODCHOL_MODE_STRICT && n > 16));
+    const bool auto_wsm =
+        wsm_ok && (!reg_ok || (mode == MODCHOL_MODE_STRICT && n > 16 && algo != MODCHOL_GMW81));
     if (wsm_ok && (pref == 2 || (pref == 0 && auto_wsm) || !reg_ok))
         return kClsWarpSmem;
     if (reg_ok)

@@ -29,11 +29,13 @@ MODCHOL_DECL_WARP(1, 0)
 MODCHOL_DECL_WARP(2, 1)
 MODCHOL_DECL_WARP(2, 0)
 
-// shared-memory-resident warp kernels (wsm_se.cuh), SE90 / SE99, n <= 64; defined in wsm_inst.cu
+// shared-memory-resident warp kernels (wsm_se.cuh, wsm_gmw.cuh), n <= 64; defined in wsm_inst.cu
 #define MODCHOL_DECL_WSM(A, S)                                                                   \
     cudaError_t launch_wsm_a##A##_s##S(int n, long long batch, const double* a, double* l,       \
                                        double* e, unsigned long long* p, int* k, int sms,        \
                                        cudaStream_t st);
+MODCHOL_DECL_WSM(0, 1)
+MODCHOL_DECL_WSM(0, 0)
 MODCHOL_DECL_WSM(1, 1)
 MODCHOL_DECL_WSM(1, 0)
 MODCHOL_DECL_WSM(2, 1)
@@ -42,7 +44,7 @@ MODCHOL_DECL_WSM(2, 0)
 inline bool wsm_kernel_available(int algo, int mode, int n)
 {
     (void)mode;
-    return n >= 1 && n <= 64 && (algo == 1 || algo == 2);
+    return n >= 1 && n <= 64 && algo >= 0 && algo <= 2;
 }
 
 inline cudaError_t launch_wsm_kernel(int algo, int mode, int n, long long batch, const double* a,
@@ -50,6 +52,9 @@ inline cudaError_t launch_wsm_kernel(int algo, int mode, int n, long long batch,
                                      cudaStream_t st)
 {
     const bool strict = mode == 0;
+    if (algo == 0)
+        return strict ? launch_wsm_a0_s1(n, batch, a, l, e, p, k, sms, st)
+                      : launch_wsm_a0_s0(n, batch, a, l, e, p, k, sms, st);
     if (algo == 1)
         return strict ? launch_wsm_a1_s1(n, batch, a, l, e, p, k, sms, st)
                       : launch_wsm_a1_s0(n, batch, a, l, e, p, k, sms, st);

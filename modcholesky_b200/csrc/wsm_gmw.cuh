@@ -1,0 +1,246 @@
+// wsm_gmw.cuh -- GMW81 (gmw81.rs:39-134) with the matrix resident in shared memory: one warp per
+// matrix, packed lower triangle, lane = permuted position, R rows per lane (n <= 32 R).
+// Same storage and swap as wsm_se.cuh; LEFT-looking like the reference so that STRICT mode
+// reproduces every rounding:
+//   W(i,s), s <  j : c_is for the rows i >= j still to be eliminated (gmw81.rs:84); for a
+//                    finished row i < j the FINAL L entry l_is * sqrt(d_s) (gmw81.rs:112-125)
+//   W(i,s), s >= j : the permuted input (never modified by the reference either)
+//   cd             : running diagonal of c (gmw81.rs:104-109), per row
+//   dpos/sqd/rdpos : d_s, sqrt(d_s), 1/d_s for the position s == this lane's row (rows ARE
+//                    positions here, so the same lane that owns row s owns column s's d)
+#pragma once
+#include "wsm_se.cuh"
+
+namespace modchol {
+
+// sum_{s<j} line[s] * W(i,s) for one row (byte address rowb), ndarray order or FMA chains
+template <bool kStrict>
+__device__ __forceinline__ double wsm_gmw_dot(unsigned lineb, unsigned rowb, int j)
+{
+    if constexpr (kStrict) {
+        double p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            p[u] = 0.0;
+        int s = 0;
+        for (; s + 8 <= j; s += 8) {
+            double l[8], w[8];
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                const double2 v = lds_v2f64(lineb + 8u * (s + u));
+                l[u] = v.x;
+                l[u + 1] = v.y;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                w[u] = lds_f64(rowb + 8u * (s + u));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                p[u] = dadd(p[u], dmul(l[u], w[u]));
+        }
+        double acc = 0.0;
+        acc = dadd(acc, dadd(p[0], p[4]));
+        acc = dadd(acc, dadd(p[1], p[5]));
+        acc = dadd(acc, dadd(p[2], p[6]));
+        acc = dadd(acc, dadd(p[3], p[7]));
+        for (; s < j; ++s)
+            acc = dadd(acc, dmul(lds_f64(lineb + 8u * s), lds_f64(rowb + 8u * s)));
+        return acc;
+    } else {
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        int s = 0;
+        for (; s + 4 <= j; s += 4) {
+            const double2 l01 = lds_v2f64(lineb + 8u * s), l23 = lds_v2f64(lineb + 8u * s + 16);
+            double w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                w[u] = lds_f64(rowb + 8u * (s + u));
+            a[0] = __fma_rn(l01.x, w[0], a[0]);
+            a[1] = __fma_rn(l01.y, w[1], a[1]);
+            a[2] = __fma_rn(l23.x, w[2], a[2]);
+            a[3] = __fma_rn(l23.y, w[3], a[3]);
+        }
+        for (; s < j; ++s)
+            a[0] = __fma_rn(lds_f64(lineb + 8u * s), lds_f64(rowb + 8u * s), a[0]);
+        return dadd(dadd(a[0], a[1]), dadd(a[2], a[3]));
+    }
+}
+
+template <int R, bool kStrict, int kWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
+wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
+               double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
+               int* __restrict__ K)
+{
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* W = sm + (size_t)wib * wstride;
+    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);
+    const unsigned scrb = wb + 8u * (unsigned)((tri(n) + 1) & ~1);
+    const unsigned lineb = scrb + 128u;
+    const size_t nn = (size_t)n * n;
+    const long long nwarps = (long long)gridDim.x * kWarps;
+
+    int row[R];
+    unsigned tib[R];
+    bool rv[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        row[s] = lane + 32 * s;
+        rv[s] = row[s] < n;
+        tib[s] = wb + 8u * (unsigned)tri(rv[s] ? row[s] : 0);
+    }
+
+    for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nwarps) {
+        const double* Ab = A + (size_t)b * nn;
+        // ---- load the lower triangle; off-diagonal maximum on the fly (gmw81.rs:52-58) --------
+        __syncwarp();
+        double om = 0.0;
+        for (int i0 = 0; i0 < n; i0 += 8) {
+            double v[8][R];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = i0 + u, k = lane + 32 * s;
+                    v[u][s] = (i < n && k <= i) ? __ldg(Ab + i * n + k) : 0.0;
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = i0 + u, k = lane + 32 * s;
+                    sts_f64_if(i < n && k <= i, wb + 8u * (unsigned)(tri(i) + k), v[u][s]);
+                    if (i < n && k < i)
+                        om = fmax(om, fabs(v[u][s]));
+                }
+        }
+        __syncwarp();
+
+        double cd[R], ev[R], dpos[R], sqd[R], rdpos[R], av[R], omv[R], dummy[R];
+        int perm[R];
+        bool win[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            cd[s] = rv[s] ? lds_f64(tib[s] + 8u * row[s]) : 0.0;   // gmw81.rs:66-67
+            ev[s] = 0.0;
+            dpos[s] = sqd[s] = rdpos[s] = 0.0;
+            dummy[s] = 0.0;
+            perm[s] = row[s];
+            av[s] = fabs(cd[s]);
+            omv[s] = om;
+        }
+        bool all[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            all[s] = s == 0;
+        // gmw81.rs:49-64 (A symmetric: the lower off-diagonals carry the off-diagonal maximum)
+        const double diag_max = wsm_extreme<true, R>(av, rv, 0.0, win);
+        const double off_max = wsm_extreme<true, R>(omv, all, 0.0, win);
+        const double nf = (double)n;
+        const double delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(diag_max, off_max)));
+        const double beta =
+            dsqrt(fmax(fmax(diag_max, ddiv(off_max, dsqrt(dsub(dmul(nf, nf), 1.0)))), MODCHOL_EPS));
+        const double rbeta = kStrict ? 0.0 : ddiv(1.0, beta);
+
+        unsigned tjb = wb;
+        for (int j = 0; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+            // ---- pivot on max |c_ii| (gmw81.rs:71-78) ---------------------------------------
+            bool active[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                active[s] = rv[s] && row[s] >= j;
+                av[s] = fabs(cd[s]);
+            }
+            double best;
+            const int m = wsm_argmax_first<R>(av, active, row, j, best);
+            if (m != j)
+                wsm_swap_positions<R>(wb, scrb, tib, row, rv, lane, j, m, tjb, cd, dummy, perm);
+            // ---- l_js = c_js / d_s, s < j (gmw81.rs:79-81): lane s owns d_s -----------------
+            double ljs[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                ljs[s] = 0.0;
+                if (rv[s] && row[s] < j) {
+                    const double cjs = lds_f64(tjb + 8u * row[s]);
+                    ljs[s] = kStrict ? ddiv(cjs, dpos[s]) : dmul(cjs, rdpos[s]);
+                    sts_f64(lineb + 8u * row[s], ljs[s]);
+                }
+            }
+            __syncwarp();
+            // ---- c_ij = l_ij - sum_s l_js c_is for i >= j (gmw81.rs:83-85) ------------------
+            double cij[R], acij[R];
+            bool below[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                below[s] = rv[s] && row[s] > j;
+                cij[s] = 0.0;
+                if (rv[s] && row[s] >= j) {
+                    const double acc = wsm_gmw_dot<kStrict>(lineb, tib[s], j);
+                    cij[s] = dsub(lds_f64(tib[s] + 8u * j), acc);
+                }
+                acij[s] = fabs(cij[s]);
+            }
+            // theta = max_{i>j} |c_ij|, 0 for the last column (gmw81.rs:87-100)
+            const double theta = wsm_extreme<true, R>(acij, below, 0.0, win);
+            const double cjj = wsm_bcast_row<R>(cij, j);
+            const double tb = kStrict ? ddiv(theta, beta) : dmul(theta, rbeta);
+            const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
+            double sq, rdj = 0.0;
+            const bool fast = !kStrict && fast_range_ok(dj);
+            if (fast) {
+                const double y = rsqrt_normal(dj);
+                sq = dmul(dj, y);
+                rdj = dmul(y, y);
+            } else {
+                sq = dsqrt(dj);
+                if (!kStrict)
+                    rdj = ddiv(1.0, dj);
+            }
+            __syncwarp();   // row j's lane has read its c_js (dot product) before they are replaced
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                // row j is final from here on: L_js = l_js * sqrt(d_s); the reference's dense dot
+                // adds exact zeros, which only turns a -0 into +0 (gmw81.rs:112-125)
+                if (rv[s] && row[s] < j)
+                    sts_f64(tjb + 8u * row[s], dadd(0.0, dmul(ljs[s], sqd[s])));
+                if (below[s]) {
+                    sts_f64(tib[s] + 8u * j, cij[s]);
+                    const double c2 = dmul(cij[s], cij[s]);   // gmw81.rs:104-109
+                    cd[s] = kStrict ? dsub(cd[s], ddiv(c2, dj)) : __fma_rn(-c2, rdj, cd[s]);
+                }
+                if (row[s] == j) {
+                    ev[s] = dsub(dj, cjj);                                   // gmw81.rs:110
+                    sts_f64(tjb + 8u * j, dadd(0.0, dmul(1.0, sq)));         // L_jj = sqrt(d_j)
+                    dpos[s] = dj;
+                    sqd[s] = sq;
+                    rdpos[s] = rdj;
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- epilogue ---------------------------------------------------------------------
+        double* Lb = L + (size_t)b * nn;
+        for (int i0 = 0; i0 < n; i0 += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const int i = i0 + u, k = lane + 32 * s;
+                    if (i < n && k < n)
+                        Lb[i * n + k] = (k <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + k)) : 0.0;
+                }
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            if (rv[s]) {
+                E[(size_t)b * n + perm[s]] = ev[s];                          // gmw81.rs:127-131
+                P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
+            }
+        if (K && lane == 0)
+            K[b] = -1;
+    }
+}
+
+}  // namespace modchol

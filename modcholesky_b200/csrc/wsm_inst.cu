@@ -1,6 +1,7 @@
 // wsm_inst.cu -- instantiates the shared-memory-resident warp kernels (wsm_se.cuh) for ONE
 // (algorithm, mode) pair: -DMODCHOL_INST_ALGO={1,2} -DMODCHOL_INST_STRICT={0,1}.
 #include "warp_kernels.cuh"
+#include "wsm_gmw.cuh"
 #include "wsm_se.cuh"
 
 #ifndef MODCHOL_WSM_MINB
@@ -18,7 +19,12 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
 {
     constexpr int kWarps = 4;
     constexpr int kMinBlocks = R == 1 ? MODCHOL_WSM_MINB : 3;
-    auto kern = wsm_se_kernel<kAlgo, R, kStrict, kWarps, kMinBlocks>;
+    auto kern = [] {
+        if constexpr (kAlgo == kGMW81)
+            return wsm_gmw_kernel<R, kStrict, kWarps, kMinBlocks>;
+        else
+            return wsm_se_kernel<kAlgo, R, kStrict, kWarps, kMinBlocks>;
+    }();
     const int wstride = wsm_warp_doubles(n);
     const size_t smem = (size_t)kWarps * wstride * sizeof(double);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -162,6 +162,83 @@ __device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, 
     return acc;
 }
 
+// Symmetric exchange of positions j < m in the packed lower triangle (utils.rs:30-49):
+//   i < j     : (j,i) <-> (m,i)        i == j : (j,j) <-> (m,m)
+//   j < i < m : (i,j) <-> (m,i)        i == m : (m,j) stays        i > m : (i,j) <-> (i,m)
+// wb = byte address of W(0,0), tjb = byte address of W(j,0), tib[s] = byte address of W(row,0).
+// Branch free: two address selects, two loads, two predicated stores per row.  The per-row
+// scalars (x, y, perm) of positions j and m are exchanged by shuffle (R == 1) or through the
+// scratch line at scrb (R == 2).
+template <int R>
+__device__ __forceinline__ void wsm_swap_positions(unsigned wb, unsigned scrb, const unsigned (&tib)[R],
+                                                   const int (&row)[R], const bool (&rv)[R], int lane,
+                                                   int j, int m, unsigned tjb, double (&x)[R],
+                                                   double (&y)[R], int (&perm)[R])
+{
+    const unsigned tmb = wb + 8u * (unsigned)tri(m);
+    unsigned a1[R], a2[R];
+    double t1[R], t2[R];
+    bool act[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int i = row[s];
+        act[s] = rv[s] && i != m;
+        a1[s] = (i <= j) ? tjb + 8u * i : tib[s] + 8u * j;
+        a2[s] = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib[s] + 8u * m);
+        if (!act[s]) {
+            a1[s] = wb;
+            a2[s] = wb;
+        }
+        t1[s] = lds_f64(a1[s]);
+        t2[s] = lds_f64(a2[s]);
+    }
+    if constexpr (R == 1) {
+        const int partner = (lane == j) ? m : ((lane == m) ? j : lane);
+        x[0] = __shfl_sync(kFull, x[0], partner);
+        y[0] = __shfl_sync(kFull, y[0], partner);
+        perm[0] = __shfl_sync(kFull, perm[0], partner);
+    } else {
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const int i = row[s];
+            if (i == j || i == m) {
+                const unsigned q = scrb + (i == j ? 0u : 32u);
+                sts_f64(q, x[s]);
+                sts_f64(q + 8, y[s]);
+                sts_f64(q + 16, (double)perm[s]);
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        sts_f64_if(act[s], a1[s], t2[s]);
+        sts_f64_if(act[s], a2[s], t1[s]);
+        if constexpr (R > 1) {
+            const int i = row[s];
+            if (i == j || i == m) {
+                const unsigned q = scrb + (i == j ? 32u : 0u);
+                x[s] = lds_f64(q);
+                y[s] = lds_f64(q + 8);
+                perm[s] = (int)lds_f64(q + 16);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// value v[s] of the row at position j, broadcast to the warp
+template <int R>
+__device__ __forceinline__ double wsm_bcast_row(const double (&v)[R], int j)
+{
+    double x = v[0];
+#pragma unroll
+    for (int s = 1; s < R; ++s)
+        if ((j >> 5) == s)
+            x = v[s];
+    return __shfl_sync(kFull, x, j & 31);
+}
+
 template <int kAlgo, int R, bool kStrict, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
@@ -228,75 +305,11 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         double delta_prev = 0.0;
         int kstart = -1;
 
-        // symmetric exchange of positions j < m in the packed lower triangle (utils.rs:30-49):
-        //   i < j     : (j,i) <-> (m,i)        i == j : (j,j) <-> (m,m)
-        //   j < i < m : (i,j) <-> (m,i)        i == m : (m,j) stays        i > m : (i,j) <-> (i,m)
-        // tjb = byte address of W(j,0).  Branch free: two address selects, two loads, two
-        // predicated stores per row; the row scalars of positions j and m are exchanged by
-        // shuffle (R == 1) or through the scratch line (R == 2).
-        auto swap_positions = [&](int j, int m, unsigned tjb, bool with_g) {
-            const unsigned tmb = wb + 8u * (unsigned)tri(m);
-            unsigned a1[R], a2[R];
-            double t1[R], t2[R];
-            bool act[R];
-#pragma unroll
-            for (int s = 0; s < R; ++s) {
-                const int i = row[s];
-                act[s] = rv[s] && i != m;
-                a1[s] = (i <= j) ? tjb + 8u * i : tib[s] + 8u * j;
-                a2[s] = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib[s] + 8u * m);
-                if (!act[s]) {
-                    a1[s] = wb;
-                    a2[s] = wb;
-                }
-                t1[s] = lds_f64(a1[s]);
-                t2[s] = lds_f64(a2[s]);
-            }
-            if constexpr (R == 1) {
-                const int partner = (lane == j) ? m : ((lane == m) ? j : lane);
-                dg[0] = __shfl_sync(kFull, dg[0], partner);
-                if (with_g)
-                    g[0] = __shfl_sync(kFull, g[0], partner);
-                perm[0] = __shfl_sync(kFull, perm[0], partner);
-            } else {
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int i = row[s];
-                    if (i == j || i == m) {
-                        const unsigned q = scrb + (i == j ? 0u : 32u);
-                        sts_f64(q, dg[s]);
-                        sts_f64(q + 8, g[s]);
-                        sts_f64(q + 16, (double)perm[s]);
-                    }
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int s = 0; s < R; ++s) {
-                sts_f64_if(act[s], a1[s], t2[s]);
-                sts_f64_if(act[s], a2[s], t1[s]);
-                if constexpr (R > 1) {
-                    const int i = row[s];
-                    if (i == j || i == m) {
-                        const unsigned q = scrb + (i == j ? 32u : 0u);
-                        dg[s] = lds_f64(q);
-                        if (with_g)
-                            g[s] = lds_f64(q + 8);
-                        perm[s] = (int)lds_f64(q + 16);
-                    }
-                }
-            }
-            __syncwarp();
+        // exchange of positions j < m: packed triangle + the row scalars dg, g, perm
+        auto swap_positions = [&](int j, int m, unsigned tjb, bool /*with_g*/) {
+            wsm_swap_positions<R>(wb, scrb, tib, row, rv, lane, j, m, tjb, dg, g, perm);
         };
-        // value v[s] of the row at position j, broadcast to the warp
-        auto bcast_row = [&](const double (&v)[R], int j) -> double {
-            double x = v[0];
-#pragma unroll
-            for (int s = 1; s < R; ++s)
-                if ((j >> 5) == s)
-                    x = v[s];
-            return __shfl_sync(kFull, x, j & 31);
-        };
+        auto bcast_row = [&](const double (&v)[R], int j) -> double { return wsm_bcast_row<R>(v, j); };
         // D: s = sqrt(pivot), y such that cs = col*y (FAST) -- see warp_se.cuh
         auto scale = [&](double piv, double& sq, double& y, double& inv_piv) -> bool {
             const bool fast = !kStrict && fast_range_ok(piv);

@@ -130,7 +130,7 @@ def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
     family (default for 32 < n <= 64) must give the same bits there too."""
     prev = m.set_small_kernel_family(family)
     try:
-        for algo in ("se90", "se99"):
+        for algo in ALGOS:
             for n in (1, 2, 5, 8, 16, 17, 31, 32):
                 for mode in ("strict", "fast"):
                     assert m.kernel_class(algo, n, mode) == ("warp32" if family == "reg" else "warp_smem")
