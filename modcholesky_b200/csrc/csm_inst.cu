@@ -1,0 +1,47 @@
+// csm_inst.cu -- instantiates the block-per-matrix packed shared-memory kernels (csm_se.cuh) for
+// ONE (algorithm, mode) pair: -DMODCHOL_INST_ALGO={1,2} -DMODCHOL_INST_STRICT={0,1}.
+#include "warp_kernels.cuh"
+#include "csm_se.cuh"
+
+#ifndef MODCHOL_INST_ALGO
+#error "compile with -DMODCHOL_INST_ALGO=.. -DMODCHOL_INST_STRICT=.."
+#endif
+
+namespace modchol {
+
+template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks>
+static cudaError_t launch_csm(int n, long long batch, const double* a, double* l, double* e,
+                              unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    auto kern = csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks>;
+    const size_t smem = csm_smem_bytes(n);
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              (int)cudaSharedmemCarveoutMaxShared);
+    if (ce != cudaSuccess) return ce;
+    int occ = 1;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+    if (ce != cudaSuccess) return ce;
+    if (occ < 1) occ = 1;
+    long long blocks = batch;
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;   // persistent: every block strides over the batch
+    kern<<<(unsigned)blocks, kThreads, smem, st>>>(n, batch, a, l, e, p, k);
+    return cudaGetLastError();
+}
+
+#define MODCHOL_CAT2(a, b, c, d) a##b##c##d
+#define MODCHOL_CAT(a, b, c, d) MODCHOL_CAT2(a, b, c, d)
+cudaError_t MODCHOL_CAT(launch_csm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT)(
+    int n, long long batch, const double* a, double* l, double* e, unsigned long long* p, int* k,
+    int sms, cudaStream_t st)
+{
+    constexpr int A = MODCHOL_INST_ALGO;
+    constexpr bool S = MODCHOL_INST_STRICT != 0;
+    if (n <= 128)
+        return launch_csm<A, S, 128, 3>(n, batch, a, l, e, p, k, sms, st);
+    return launch_csm<A, S, 256, 1>(n, batch, a, l, e, p, k, sms, st);
+}
+
+}  // namespace modchol

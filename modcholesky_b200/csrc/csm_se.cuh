@@ -1,0 +1,432 @@
+// csm_se.cuh -- SE90 / SE99, one thread BLOCK per matrix, matrix resident in shared memory as a
+// packed lower triangle, thread = permuted position (row).  The block-level sibling of
+// wsm_se.cuh for 64 < n <= kThreads (<= 208 with 227 KB of shared memory):
+//   * same storage (element (i,k) at T(i)+k, conflict-free column access), same branch-free
+//     symmetric swap, same lower-triangle-only update, same STRICT / FAST arithmetic;
+//   * warp collectives become two-level: REDUX inside each warp, one double-buffered exchange
+//     line in shared memory and ONE __syncthreads per collective;
+//   * n = 128 needs 66 KB instead of the 133 KB of the full-square CTA kernel: three blocks
+//     per SM instead of one.
+#pragma once
+#include "wsm_se.cuh"
+
+namespace modchol {
+
+constexpr int kCsmMaxWarps = 8;
+
+// exchange area: 2 buffers x (8 hi, 8 lo, 8 pos, 8 flags) ints + 2 x 8 doubles + 8 scalars
+struct CsmScratch {
+    int* ints;        // [2][4][8]
+    double* dbl;      // [2][8]
+    double* scal;     // [8]
+    int buf;
+};
+__host__ __device__ inline int csm_scratch_doubles() { return 32 + 16 + 8; }
+
+__device__ __forceinline__ CsmScratch csm_scratch(double* base)
+{
+    CsmScratch s;
+    s.ints = reinterpret_cast<int*>(base);
+    s.dbl = base + 32;
+    s.scal = base + 48;
+    s.buf = 0;
+    return s;
+}
+
+// Block-wide extreme with the NaN rules of warp_extreme; one __syncthreads.
+template <bool kMax>
+__device__ __forceinline__ double csm_extreme(CsmScratch& sc, int nwarps, double v, bool cand,
+                                              double none, bool& win)
+{
+    int khi;
+    unsigned klo;
+    make_key(v, khi, klo);
+    cand = cand && (v == v);
+    if (!kMax) {
+        khi = ~khi;
+        klo = ~klo;
+    }
+    const int INT_MIN_ = (int)0x80000000;
+    const int wh = __reduce_max_sync(kFull, cand ? khi : INT_MIN_);
+    const unsigned wl = __reduce_max_sync(kFull, (cand && khi == wh) ? klo : 0u);
+    int* I = sc.ints + sc.buf * 32;
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        I[warp] = wh;
+        I[8 + warp] = (int)wl;
+    }
+    __syncthreads();
+    int gh = INT_MIN_;
+    unsigned gl = 0u;
+    for (int w = 0; w < nwarps; ++w) {
+        const int h = I[w];
+        const unsigned l = (unsigned)I[8 + w];
+        if (h > gh || (h == gh && l > gl)) {
+            gh = h;
+            gl = l;
+        }
+    }
+    sc.buf ^= 1;
+    win = cand && khi == gh && klo == gl;
+    if (gh == INT_MIN_)
+        return none;
+    return kMax ? key_value(gh, gl) : key_value(~gh, ~gl);
+}
+
+// First-strict-maximum pivot search over rows [lo, n) (utils.rs:52-91); one __syncthreads.
+__device__ __forceinline__ int csm_argmax_first(CsmScratch& sc, int nwarps, double v, bool active,
+                                                int row, int lo, double& best)
+{
+    int khi;
+    unsigned klo;
+    make_key(v, khi, klo);
+    const bool cand = active && (v == v);
+    const int INT_MIN_ = (int)0x80000000;
+    const int wh = __reduce_max_sync(kFull, cand ? khi : INT_MIN_);
+    const bool c1 = cand && khi == wh;
+    const unsigned wl = __reduce_max_sync(kFull, c1 ? klo : 0u);
+    const unsigned wp = __reduce_min_sync(kFull, (c1 && klo == wl) ? (unsigned)row : 0xffffu);
+    const unsigned hn = __ballot_sync(kFull, active && row == lo && (v != v));
+    int* I = sc.ints + sc.buf * 32;
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        I[warp] = wh;
+        I[8 + warp] = (int)wl;
+        I[16 + warp] = (int)wp;
+        I[24 + warp] = hn != 0u;
+    }
+    __syncthreads();
+    int gh = INT_MIN_, gp = 0xffff, head_nan = 0;
+    unsigned gl = 0u;
+    for (int w = 0; w < nwarps; ++w) {
+        const int h = I[w], p = I[16 + w];
+        const unsigned l = (unsigned)I[8 + w];
+        head_nan |= I[24 + w];
+        if (h > gh || (h == gh && l > gl)) {
+            gh = h;
+            gl = l;
+            gp = p;
+        } else if (h == gh && l == gl && p < gp) {
+            gp = p;
+        }
+    }
+    sc.buf ^= 1;
+    best = (gh == INT_MIN_) ? -INFINITY : key_value(gh, gl);
+    if (head_nan || gh == INT_MIN_ || gp >= 0xffff)
+        gp = lo;
+    return gp;
+}
+
+// block-wide sum (tree order); one __syncthreads
+__device__ __forceinline__ double csm_sum_tree(CsmScratch& sc, int nwarps, double x)
+{
+    x = warp_sum_tree<32>(kFull, x);
+    double* D = sc.dbl + sc.buf * 8;
+    if ((threadIdx.x & 31) == 0)
+        D[threadIdx.x >> 5] = x;
+    __syncthreads();
+    double s = D[0];
+    for (int w = 1; w < nwarps; ++w)
+        s = dadd(s, D[w]);
+    sc.buf ^= 1;
+    return s;
+}
+
+template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
+              double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    extern __shared__ double sm[];
+    double* W = sm;
+    const int tpad = (tri(n) + 1) & ~1;
+    double* linep = W + tpad;                       // n + 8 entries (scaled pivot column)
+    const int lpad = (n + 8 + 1) & ~1;
+    CsmScratch sc = csm_scratch(linep + lpad);
+    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);
+    const unsigned lineb = wb + 8u * (unsigned)tpad;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nwarps = kThreads >> 5;
+    const size_t nn = (size_t)n * n;
+    const int row = tid;
+    const bool rv = row < n;
+    const unsigned tib = wb + 8u * (unsigned)tri(rv ? row : 0);
+
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const double* Ab = A + (size_t)b * nn;
+        // ---- load the lower triangle (coalesced: consecutive threads, consecutive columns) ----
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                v[u] = (i < n && tid <= i) ? __ldg(Ab + i * n + tid) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                sts_f64_if(i < n && tid <= i, wb + 8u * (unsigned)(tri(i) + tid), v[u]);
+            }
+        }
+        __syncthreads();
+
+        double dg = rv ? lds_f64(tib + 8u * row) : 0.0;
+        double g = 0.0, ev = 0.0;
+        int perm = row;
+        bool win;
+        // gamma = max |a_ii| folded from 0.0 (se90.rs:55-57, se99.rs:54-56)
+        const double gamma = csm_extreme<true>(sc, nwarps, fabs(dg), rv, 0.0, win);
+        const double taugamma = dmul(MODCHOL_TAU, gamma);
+        double delta_prev = 0.0;
+        int kstart = -1;
+
+        // symmetric exchange of positions j < m (see wsm_swap_positions) + row scalars
+        auto swap_positions = [&](int j, int m, unsigned tjb) {
+            const unsigned tmb = wb + 8u * (unsigned)tri(m);
+            const int i = row;
+            const bool act = rv && i != m;
+            unsigned a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
+            unsigned a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
+            if (!act) {
+                a1 = wb;
+                a2 = wb;
+            }
+            const double t1 = lds_f64(a1), t2 = lds_f64(a2);
+            if (i == j || i == m) {
+                double* q = sc.scal + (i == j ? 0 : 4);
+                q[0] = dg;
+                q[1] = g;
+                q[2] = (double)perm;
+            }
+            __syncthreads();
+            sts_f64_if(act, a1, t2);
+            sts_f64_if(act, a2, t1);
+            if (i == j || i == m) {
+                const double* q = sc.scal + (i == j ? 4 : 0);
+                dg = q[0];
+                g = q[1];
+                perm = (int)q[2];
+            }
+            __syncthreads();
+        };
+        auto scale = [&](double piv, double& sq, double& y, double& inv_piv) -> bool {
+            const bool fast = !kStrict && fast_range_ok(piv);
+            if (fast) {
+                y = rsqrt_normal(piv);
+                sq = dmul(piv, y);
+                inv_piv = dmul(y, y);
+            } else {
+                sq = dsqrt(piv);
+                y = 0.0;
+                inv_piv = 0.0;
+            }
+            return fast;
+        };
+        // column j of L + trailing lower-triangle update (se90.rs:84-93, se99.rs:96-105)
+        auto eliminate = [&](int j, unsigned tjb, double sq, double cs, double dg_new) {
+            const bool below = rv && row > j;
+            sts_f64_if(rv, lineb + 8u * row, cs);
+            sts_f64_if(below || row == j, below ? tib + 8u * j : tjb + 8u * j, below ? cs : sq);
+            if (below)
+                dg = dg_new;
+            __syncthreads();
+            const int k0 = (j + 1) & ~1;
+            const int c = rv ? row - j : 0;
+            const unsigned cnt = c > 0 ? (unsigned)c : 0u;
+            unsigned wr = tib + 8u * k0, lk = lineb + 8u * k0;
+            // every thread only needs columns up to its own row: warps owning early rows
+            // finish early (the loop bound is warp-uniform: the largest row of the warp)
+            const int kend = min(n, (tid | 31) + 1);
+            for (int k = k0; k < kend; k += 4) {
+                const double2 c01 = lds_v2f64(lk);
+                const double2 c23 = lds_v2f64(lk + 16);
+                const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
+                const unsigned off = (unsigned)(k - j - 1);
+                double w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    w[u] = lds_f64(wr + 8u * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    sts_f64_if(off + (unsigned)u < cnt, wr + 8u * u, nmul_add<kStrict>(w[u], cs, ck[u]));
+                wr += 32;
+                lk += 32;
+            }
+            __syncthreads();
+        };
+        // value of the row at position j, broadcast to the block (one sync)
+        auto bcast_row = [&](double v, int j) -> double {
+            double* D = sc.dbl + sc.buf * 8;
+            if (row == j)
+                D[0] = v;
+            __syncthreads();
+            sc.buf ^= 1;
+            return D[0];
+        };
+
+        // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
+        int j = 0;
+        unsigned tjb = wb;
+        for (; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+            const bool active = rv && row >= j;
+            double dmax;
+            const int m = csm_argmax_first(sc, nwarps, dg, active, row, j, dmax);
+            if (kAlgo == kSE99) {  // se99.rs:62-73
+                const double dmin = csm_extreme<false>(sc, nwarps, dg, active, INFINITY, win);
+                if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
+                    kstart = j;
+                    break;
+                }
+            }
+            if (m != j)
+                swap_positions(j, m, tjb);
+            const double piv = bcast_row(dg, j);
+            double sq, y, inv_piv;
+            const bool fast = scale(piv, sq, y, inv_piv);
+            const bool below = rv && row > j;
+            const double col = below ? lds_f64(tib + 8u * j) : 0.0;
+            const double cs = fast ? dmul(col, y) : ddiv(col, sq);
+            const double dg_new = nmul_add<kStrict>(dg, cs, cs);
+            const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
+            const double la = csm_extreme<false>(sc, nwarps, nv, below, INFINITY, win);
+            const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
+            if (la < thresh) {
+                kstart = j;
+                break;
+            }
+            eliminate(j, tjb, sq, cs, dg_new);
+        }
+
+        // ---- phase 2 ----------------------------------------------------------------------
+        if (kstart >= 0) {
+            if (kAlgo == kSE99 && kstart == n - 1) {  // se99.rs:115-119
+                const double ljj = bcast_row(dg, n - 1);
+                const double ej = tail1x1_e(ljj, gamma);
+                if (row == n - 1) {
+                    ev = ej;
+                    sts_f64(tib + 8u * row, dsqrt(dadd(ljj, ej)));
+                }
+            } else {
+                const int k0 = kstart;  // se90.rs:105-110, se99.rs:125-130
+                if (rv && row >= k0) {
+                    const int i = row, tis = tri(row);
+                    if constexpr (kStrict) {
+                        const double s1 = wsm_nd_sum_abs_lane(W, i - k0, [&](int t) { return tis + k0 + t; });
+                        const double s2 = wsm_nd_sum_abs_lane(W, n - 1 - i, [&](int t) { return tri(i + 1 + t) + i; });
+                        g = dsub(dsub(dg, s1), s2);
+                    } else {
+                        double s1 = 0.0, s2 = 0.0;
+                        for (int c = k0; c < i; ++c)
+                            s1 = dadd(s1, fabs(lds_f64(tib + 8u * c)));
+                        unsigned tr = wb + 8u * (unsigned)(tri(i + 1) + i);
+                        for (int r = i + 1; r < n; ++r) {
+                            s2 = dadd(s2, fabs(lds_f64(tr)));
+                            tr += 8u * (unsigned)(r + 1);
+                        }
+                        g = dsub(dg, dadd(s1, s2));
+                    }
+                }
+                for (j = k0; j + 2 < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+                    const bool active = rv && row >= j;
+                    double gmax;  // se90.rs:115, se99.rs:135
+                    const int m = csm_argmax_first(sc, nwarps, g, active, row, j, gmax);
+                    if (m != j)
+                        swap_positions(j, m, tjb);
+                    double piv = bcast_row(dg, j);
+                    const bool below = rv && row > j;
+                    const double col = below ? lds_f64(tib + 8u * j) : 0.0;
+                    const double acol = abs_bits(col);
+                    double normj;  // se90.rs:124, se99.rs:144
+                    if constexpr (kStrict) {
+                        double* D = sc.dbl + sc.buf * 8;
+                        if (tid < 32) {
+                            const double s = wsm_nd_sum_abs_col(W, j + 1, j, n - j - 1, lane);
+                            if (lane == 0)
+                                D[0] = s;
+                        }
+                        __syncthreads();
+                        sc.buf ^= 1;
+                        normj = D[0];
+                    } else {
+                        normj = csm_sum_tree(sc, nwarps, acol);
+                    }
+                    const double ej =
+                        max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
+                    if (kStrict) {
+                        if (ej > 0.0) {
+                            piv = dadd(piv, ej);
+                            delta_prev = ej;
+                        }
+                    } else {
+                        piv = dadd(piv, ej);
+                        delta_prev = ej;
+                    }
+                    double sq, y, inv_piv;
+                    const bool fast = scale(piv, sq, y, inv_piv);
+                    const bool upd = fabs(dsub(piv, normj)) > MODCHOL_EPS;  // se90.rs:134-139
+                    double t = 0.0;
+                    if (upd)
+                        t = fast ? __fma_rn(-normj, inv_piv, 1.0) : dsub(1.0, ddiv(normj, piv));
+                    if (row == j)
+                        ev = ej;
+                    const double cs = fast ? dmul(col, y) : ddiv(col, sq);
+                    const double dg_new = nmul_add<kStrict>(dg, cs, cs);
+                    if (upd && below)
+                        g = mul_add<kStrict>(g, acol, t);
+                    eliminate(j, tjb, sq, cs, dg_new);
+                }
+                // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186)
+                double a00 = bcast_row(dg, n - 2);
+                double a11 = bcast_row(dg, n - 1);
+                const unsigned a10b = wb + 8u * (unsigned)(tri(n - 1) + n - 2);
+                double a10 = lds_f64(a10b);
+                double lhi, llo;
+                eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);
+                const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
+                if (en > 0.0) {
+                    a00 = dadd(a00, en);
+                    a11 = dadd(a11, en);
+                }
+                a00 = dsqrt(a00);
+                a10 = ddiv(a10, a00);
+                a11 = dsqrt(dsub(a11, dmul(a10, a10)));
+                __syncthreads();
+                if (row == n - 2) {
+                    ev = en;
+                    sts_f64(tib + 8u * row, a00);
+                }
+                if (row == n - 1) {
+                    ev = en;
+                    sts_f64(a10b, a10);
+                    sts_f64(tib + 8u * row, a11);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- epilogue ---------------------------------------------------------------------
+        double* Lb = L + (size_t)b * nn;
+        for (int i0 = 0; i0 < n; i0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                if (i < n && tid < n)
+                    Lb[i * n + tid] = (tid <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + tid)) : 0.0;
+            }
+        }
+        if (rv) {
+            E[(size_t)b * n + perm] = ev;                            // se99.rs:194-198
+            P[(size_t)b * n + row] = (unsigned long long)perm;
+        }
+        if (K && tid == 0)
+            K[b] = kstart;
+    }
+}
+
+__host__ inline size_t csm_smem_bytes(int n)
+{
+    return (size_t)(((tri(n) + 1) & ~1) + ((n + 8 + 1) & ~1) + csm_scratch_doubles()) * sizeof(double);
+}
+
+}  // namespace modchol

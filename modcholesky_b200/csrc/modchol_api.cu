@@ -121,7 +121,7 @@ int slot_reserve(Slot& s, size_t mats, int n)
 }
 
 // ---- size-class dispatch ---------------------------------------------------------------
-enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3 };
+enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3, kClsCtaPacked = 4 };
 
 // Which small-n family serves n <= 32 (0 auto, 1 registers, 2 shared memory); initialised
 // from MODCHOL_SMALL_KERNEL=reg|wsm, changed by modchol_set_small_kernel_family().
@@ -154,6 +154,8 @@ KernelClass classify(int algo, int mode, int n, int smem_optin)
         return kClsWarpSmem;
     if (reg_ok)
         return kClsWarp;
+    if (csm_kernel_available(algo, mode, n))
+        return kClsCtaPacked;
     if (smem_optin <= 0)
         smem_optin = 227 * 1024;
     if (cta_shared_bytes(n, cta_ld(n), true) <= (size_t)smem_optin)
@@ -209,6 +211,13 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
         g_launches.fetch_add(1);
         if (ce != cudaSuccess)
             return fail(MODCHOL_ERR_CUDA, "wsm kernel launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    if (cls == kClsCtaPacked) {
+        cudaError_t ce = launch_csm_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "csm kernel launch failed: %s", cudaGetErrorString(ce));
         return MODCHOL_OK;
     }
     const bool use_smem = cls == kClsCtaSmem;
@@ -316,6 +325,7 @@ const char* modchol_kernel_class(int algo, int mode, int32_t n)
     switch (classify(algo, mode, n, 0)) {
     case kClsWarp: return "warp32";
     case kClsWarpSmem: return "warp_smem";
+    case kClsCtaPacked: return "cta_packed";
     case kClsCtaSmem: return "cta_smem";
     default: return "cta_gmem";
     }

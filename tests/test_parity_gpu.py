@@ -111,7 +111,7 @@ def test_gershgorin_circles_on_gpu(golden, oracle, torch_cuda):
     assert np.array_equal(outd, ref)
 
 
-SIZES = [1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 23, 24, 31, 32, 33, 40, 48, 63, 64, 65, 96, 128]
+SIZES = [1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 23, 24, 31, 32, 33, 40, 48, 63, 64, 65, 96, 127, 128, 129]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -146,7 +146,7 @@ def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("n", [160, 200, 256])
+@pytest.mark.parametrize("n", [160, 200, 236, 237, 256])
 def test_strict_bit_exact_large(oracle, torch_cuda, algo, n):
     for fam in ("uniform", "wishart"):
         a = matgen.make(fam, 2000 + n, 6, n)
@@ -155,9 +155,9 @@ def test_strict_bit_exact_large(oracle, torch_cuda, algo, n):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("n", [2, 3, 6, 8, 13, 16, 24, 32, 48, 64])
+@pytest.mark.parametrize("n", [2, 3, 6, 8, 13, 16, 24, 32, 48, 64, 100, 150])
 def test_fast_mode_within_north_star_tolerances(oracle, torch_cuda, algo, n):
-    b = 512 if n <= 32 else 64
+    b = 512 if n <= 32 else (64 if n <= 64 else 16)
     for fam in ("uniform", "wishart", "pd", "bench"):
         a = matgen.make(fam, 3000 + n, b, n)
         ref = oracle.factor_batched(algo, a)
