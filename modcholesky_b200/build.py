@@ -28,7 +28,7 @@ UNITS = [("modchol_api.cu", "api.o", [])] + [
     for a in (0, 1, 2) for s in (1, 0)
 ] + [
     ("csm_inst.cu", f"csm_a{a}_s{s}.o", [f"-DMODCHOL_INST_ALGO={a}", f"-DMODCHOL_INST_STRICT={s}"])
-    for a in (1, 2) for s in (1, 0)
+    for a in (0, 1, 2) for s in (1, 0)
 ]
 
 

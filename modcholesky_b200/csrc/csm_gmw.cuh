@@ -1,0 +1,171 @@
+// csm_gmw.cuh -- GMW81 (gmw81.rs:39-134), one thread block per matrix, packed lower triangle in
+// shared memory, thread = permuted position.  Block-level sibling of wsm_gmw.cuh (same storage
+// conventions: W(i,s) = c_is for s < j and i >= j, final L entries for finished rows, untouched
+// input for s >= j; LEFT-looking dot products in ndarray order) with the two-level collectives of
+// csm_se.cuh.  64 < n <= 236.
+#pragma once
+#include "csm_se.cuh"
+#include "wsm_gmw.cuh"
+
+namespace modchol {
+
+template <bool kStrict, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
+               double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    extern __shared__ double sm[];
+    double* W = sm;
+    const int tpad = (tri(n) + 1) & ~1;
+    double* linep = W + tpad;
+    const int lpad = (n + 8 + 1) & ~1;
+    CsmScratch sc = csm_scratch(linep + lpad);
+    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);
+    const unsigned lineb = wb + 8u * (unsigned)tpad;
+    const int tid = threadIdx.x;
+    const int nwarps = kThreads >> 5;
+    const size_t nn = (size_t)n * n;
+    const int row = tid;
+    const bool rv = row < n;
+    const unsigned tib = wb + 8u * (unsigned)tri(rv ? row : 0);
+
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const double* Ab = A + (size_t)b * nn;
+        // ---- load the lower triangle; off-diagonal maximum on the fly (gmw81.rs:52-58) --------
+        __syncthreads();
+        double om = 0.0;
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                v[u] = (i < n && tid <= i) ? __ldg(Ab + i * n + tid) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                sts_f64_if(i < n && tid <= i, wb + 8u * (unsigned)(tri(i) + tid), v[u]);
+                if (i < n && tid < i)
+                    om = fmax(om, fabs(v[u]));
+            }
+        }
+        __syncthreads();
+
+        double cd = rv ? lds_f64(tib + 8u * row) : 0.0;   // gmw81.rs:66-67
+        double ev = 0.0, dpos = 0.0, sqd = 0.0, rdpos = 0.0;
+        int perm = row;
+        bool win;
+        // gmw81.rs:49-64
+        const double diag_max = csm_extreme<true>(sc, nwarps, fabs(cd), rv, 0.0, win);
+        const double off_max = csm_extreme<true>(sc, nwarps, om, true, 0.0, win);
+        const double nf = (double)n;
+        const double delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(diag_max, off_max)));
+        const double beta =
+            dsqrt(fmax(fmax(diag_max, ddiv(off_max, dsqrt(dsub(dmul(nf, nf), 1.0)))), MODCHOL_EPS));
+        const double rbeta = kStrict ? 0.0 : ddiv(1.0, beta);
+
+        unsigned tjb = wb;
+        for (int j = 0; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+            // ---- pivot on max |c_ii| (gmw81.rs:71-78) ---------------------------------------
+            const bool active = rv && row >= j;
+            double best;
+            const int m = csm_argmax_first(sc, nwarps, fabs(cd), active, row, j, best);
+            if (m != j) {  // symmetric exchange of positions j < m (see wsm_swap_positions)
+                const unsigned tmb = wb + 8u * (unsigned)tri(m);
+                const int i = row;
+                const bool act = rv && i != m;
+                unsigned a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
+                unsigned a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
+                if (!act) {
+                    a1 = wb;
+                    a2 = wb;
+                }
+                const double t1 = lds_f64(a1), t2 = lds_f64(a2);
+                if (i == j || i == m) {
+                    double* q = sc.scal + (i == j ? 0 : 4);
+                    q[0] = cd;
+                    q[1] = (double)perm;
+                }
+                __syncthreads();
+                sts_f64_if(act, a1, t2);
+                sts_f64_if(act, a2, t1);
+                if (i == j || i == m) {
+                    const double* q = sc.scal + (i == j ? 4 : 0);
+                    cd = q[0];
+                    perm = (int)q[1];
+                }
+                __syncthreads();
+            }
+            // ---- l_js = c_js / d_s, s < j (gmw81.rs:79-81): thread s owns d_s ---------------
+            double ljs = 0.0;
+            if (rv && row < j) {
+                const double cjs = lds_f64(tjb + 8u * row);
+                ljs = kStrict ? ddiv(cjs, dpos) : dmul(cjs, rdpos);
+                sts_f64(lineb + 8u * row, ljs);
+            }
+            __syncthreads();
+            // ---- c_ij = l_ij - sum_s l_js c_is for i >= j (gmw81.rs:83-85) ------------------
+            const bool below = rv && row > j;
+            double cij = 0.0;
+            if (rv && row >= j)
+                cij = dsub(lds_f64(tib + 8u * j), wsm_gmw_dot<kStrict>(lineb, tib, j));
+            // theta = max_{i>j} |c_ij| (gmw81.rs:87-100); the sync inside also orders the dot
+            // product's reads of row j before the writes below
+            const double theta = csm_extreme<true>(sc, nwarps, fabs(cij), below, 0.0, win);
+            double* D = sc.dbl + sc.buf * 8;
+            if (row == j)
+                D[0] = cij;
+            __syncthreads();
+            sc.buf ^= 1;
+            const double cjj = D[0];
+            const double tb = kStrict ? ddiv(theta, beta) : dmul(theta, rbeta);
+            const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
+            double sq, rdj = 0.0;
+            const bool fast = !kStrict && fast_range_ok(dj);
+            if (fast) {
+                const double y = rsqrt_normal(dj);
+                sq = dmul(dj, y);
+                rdj = dmul(y, y);
+            } else {
+                sq = dsqrt(dj);
+                if (!kStrict)
+                    rdj = ddiv(1.0, dj);
+            }
+            // row j is final: L_js = l_js * sqrt(d_s) (+0: the dense dot of gmw81.rs:125)
+            if (rv && row < j)
+                sts_f64(tjb + 8u * row, dadd(0.0, dmul(ljs, sqd)));
+            if (below) {
+                sts_f64(tib + 8u * j, cij);
+                const double c2 = dmul(cij, cij);   // gmw81.rs:104-109
+                cd = kStrict ? dsub(cd, ddiv(c2, dj)) : __fma_rn(-c2, rdj, cd);
+            }
+            if (row == j) {
+                ev = dsub(dj, cjj);                                      // gmw81.rs:110
+                sts_f64(tjb + 8u * j, dadd(0.0, dmul(1.0, sq)));
+                dpos = dj;
+                sqd = sq;
+                rdpos = rdj;
+            }
+            __syncthreads();
+        }
+
+        // ---- epilogue ---------------------------------------------------------------------
+        double* Lb = L + (size_t)b * nn;
+        for (int i0 = 0; i0 < n; i0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                if (i < n && tid < n)
+                    Lb[i * n + tid] = (tid <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + tid)) : 0.0;
+            }
+        }
+        if (rv) {
+            E[(size_t)b * n + perm] = ev;                                // gmw81.rs:127-131
+            P[(size_t)b * n + row] = (unsigned long long)perm;
+        }
+        if (K && tid == 0)
+            K[b] = -1;
+    }
+}
+
+}  // namespace modchol

@@ -1,6 +1,7 @@
 // csm_inst.cu -- instantiates the block-per-matrix packed shared-memory kernels (csm_se.cuh) for
 // ONE (algorithm, mode) pair: -DMODCHOL_INST_ALGO={1,2} -DMODCHOL_INST_STRICT={0,1}.
 #include "warp_kernels.cuh"
+#include "csm_gmw.cuh"
 #include "csm_se.cuh"
 
 #ifndef MODCHOL_INST_ALGO
@@ -13,7 +14,12 @@ template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks>
 static cudaError_t launch_csm(int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
-    auto kern = csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks>;
+    auto kern = [] {
+        if constexpr (kAlgo == kGMW81)
+            return csm_gmw_kernel<kStrict, kThreads, kMinBlocks>;
+        else
+            return csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks>;
+    }();
     const size_t smem = csm_smem_bytes(n);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;

@@ -64,12 +64,14 @@ inline cudaError_t launch_wsm_kernel(int algo, int mode, int n, long long batch,
     return cudaErrorNotSupported;
 }
 
-// block-per-matrix packed shared-memory kernels (csm_se.cuh), SE90 / SE99, 64 < n <= 236;
+// block-per-matrix packed shared-memory kernels (csm_se.cuh, csm_gmw.cuh), 64 < n <= 236;
 // defined in csm_inst.cu
 #define MODCHOL_DECL_CSM(A, S)                                                                   \
     cudaError_t launch_csm_a##A##_s##S(int n, long long batch, const double* a, double* l,       \
                                        double* e, unsigned long long* p, int* k, int sms,        \
                                        cudaStream_t st);
+MODCHOL_DECL_CSM(0, 1)
+MODCHOL_DECL_CSM(0, 0)
 MODCHOL_DECL_CSM(1, 1)
 MODCHOL_DECL_CSM(1, 0)
 MODCHOL_DECL_CSM(2, 1)
@@ -80,7 +82,7 @@ constexpr int kCsmMaxN = 236;   // packed triangle + line + scratch <= 227 KB
 inline bool csm_kernel_available(int algo, int mode, int n)
 {
     (void)mode;
-    return n > 64 && n <= kCsmMaxN && (algo == 1 || algo == 2);
+    return n > 64 && n <= kCsmMaxN && algo >= 0 && algo <= 2;
 }
 
 inline cudaError_t launch_csm_kernel(int algo, int mode, int n, long long batch, const double* a,
@@ -88,6 +90,9 @@ inline cudaError_t launch_csm_kernel(int algo, int mode, int n, long long batch,
                                      cudaStream_t st)
 {
     const bool strict = mode == 0;
+    if (algo == 0)
+        return strict ? launch_csm_a0_s1(n, batch, a, l, e, p, k, sms, st)
+                      : launch_csm_a0_s0(n, batch, a, l, e, p, k, sms, st);
     if (algo == 1)
         return strict ? launch_csm_a1_s1(n, batch, a, l, e, p, k, sms, st)
                       : launch_csm_a1_s0(n, batch, a, l, e, p, k, sms, st);
