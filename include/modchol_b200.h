@@ -109,6 +109,13 @@ int modchol_verify_batched_f64(int64_t batch, int32_t n, const double *a, const 
                                const double *e, const uint64_t *p, double *resid,
                                int32_t *flags, int mem_kind, void *stream);
 
+/* The step after the path (the caller's Newton step): solve (A + E) x = b for `nrhs` right-hand
+ * sides per matrix from a factorisation {l, p} produced above:  L L^T (P x) = P b.
+ *   b, x : batch x nrhs x n f64 (each right-hand side contiguous); x may alias b. */
+int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const double *l,
+                              const uint64_t *p, const double *b, double *x, int mem_kind,
+                              void *stream);
+
 /* Name of the kernel class the dispatcher uses for (algo, mode, n) -- e.g. "warp32",
  * "cta_smem", "cta_gmem" -- for logging and tests.  Never NULL. */
 const char *modchol_kernel_class(int algo, int mode, int32_t n);

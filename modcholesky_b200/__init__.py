@@ -11,7 +11,7 @@ from ._lib import (  # noqa: F401
 from .api import (  # noqa: F401
     Array2, Array3, Decomposition, GershgorinCircles, ModCholeskyGMW81, ModCholeskySE90,
     ModCholeskySE99, NotSquareError, factor, factor_batched, gershgorin_circles_batched,
-    mod_cholesky_gmw81, mod_cholesky_se90, mod_cholesky_se99, verify_batched)
+    mod_cholesky_gmw81, mod_cholesky_se90, mod_cholesky_se99, solve_batched, verify_batched)
 
 __version__ = "0.1.0"
 

@@ -181,6 +181,34 @@ def verify_batched(a, d: Decomposition):
     return resid, flags
 
 
+def solve_batched(d: Decomposition, b):
+    """Solve (A + E) x = b from a batched Decomposition (the Newton step of the reference's
+    callers): `b` is (batch, n) or (batch, nrhs, n); returns x of the same shape and kind."""
+    L = _lib.lib()
+    squeeze = b.ndim == 2
+    if squeeze:
+        b = b[:, None, :]
+    bt, nrhs, n = b.shape
+    if _is_torch(b):
+        import torch
+        b = b.contiguous()
+        with torch.cuda.device(b.device):
+            x = torch.empty_like(b)
+            st = torch.cuda.current_stream(b.device).cuda_stream
+            rc = L.modchol_solve_batched_f64(bt, n, nrhs, d.l.contiguous().data_ptr(),
+                                             d.p.contiguous().data_ptr(), b.data_ptr(), x.data_ptr(),
+                                             _lib.MEM_DEVICE, ctypes.c_void_p(st))
+        _lib.check(rc)
+    else:
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        l = np.ascontiguousarray(d.l, dtype=np.float64)
+        p = np.ascontiguousarray(d.p, dtype=np.uint64)
+        x = np.empty_like(b)
+        _lib.check(L.modchol_solve_batched_f64(bt, n, nrhs, l.ctypes.data, p.ctypes.data,
+                                               b.ctypes.data, x.ctypes.data, _lib.MEM_HOST, None))
+    return x[:, 0, :] if squeeze else x
+
+
 # ---- the reference's trait spelling -----------------------------------------------------
 class ModCholeskyGMW81:
     """gmw81.rs:24-32: the default body panics with "Not implemented!"."""

@@ -106,4 +106,53 @@ verify_kernel(long long batch, int n, const double* __restrict__ A, const double
     }
 }
 
+// Batched solve (A + E) x = b from a factorisation {l, p}:  P (A+E) P^T = L L^T with
+// P[i, p[i]] = 1, so  L L^T (P x) = P b.  One warp per (matrix, right-hand side):
+//   y_i = b[p_i];  forward  L z = y  in dot form (row i of L: contiguous, coalesced);
+//   backward  L^T w = z  in axpy form (again row i of L);  x[p_i] = w_i.
+// The working vector lives in shared memory (n doubles per warp).
+__global__ void __launch_bounds__(128)
+solve_kernel(long long batch, int n, int nrhs, const double* __restrict__ L,
+             const unsigned long long* __restrict__ P, const double* __restrict__ B,
+             double* __restrict__ X)
+{
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* z = sm + (size_t)wib * n;
+    const long long total = batch * (long long)nrhs;
+    for (long long t = (long long)blockIdx.x * wpb + wib; t < total; t += (long long)gridDim.x * wpb) {
+        const long long b = t / nrhs;
+        const double* l = L + (size_t)b * n * n;
+        const unsigned long long* p = P + (size_t)b * n;
+        const double* rhs = B + (size_t)t * n;
+        double* x = X + (size_t)t * n;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32)
+            z[i] = rhs[p[i]];
+        __syncwarp();
+        for (int i = 0; i < n; ++i) {  // forward substitution
+            double acc = 0.0;
+            for (int k = lane; k < i; k += 32)
+                acc = __fma_rn(l[(size_t)i * n + k], z[k], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0)
+                z[i] = (z[i] - acc) / l[(size_t)i * n + i];
+            __syncwarp();
+        }
+        for (int i = n - 1; i >= 0; --i) {  // backward substitution
+            const double wi = z[i] / l[(size_t)i * n + i];
+            __syncwarp();
+            for (int k = lane; k < i; k += 32)
+                z[k] = __fma_rn(-l[(size_t)i * n + k], wi, z[k]);
+            if (lane == 0)
+                z[i] = wi;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32)
+            x[p[i]] = z[i];
+    }
+}
+
 }  // namespace modchol

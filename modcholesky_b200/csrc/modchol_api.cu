@@ -527,4 +527,60 @@ int modchol_verify_batched_f64(int64_t batch, int32_t n, const double* a, const 
     return MODCHOL_OK;
 }
 
+int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const double* l,
+                              const uint64_t* p, const double* b, double* x, int mem_kind,
+                              void* stream)
+{
+    g_err.clear();
+    if (batch < 0 || n < 1 || nrhs < 1 || (batch > 0 && (!l || !p || !b || !x)))
+        return fail(MODCHOL_ERR_BAD_ARG, "bad argument");
+    if (n > MODCHOL_MAX_N)
+        return fail(MODCHOL_ERR_UNSUPPORTED, "n too large");
+    if (device_count() < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (batch == 0)
+        return MODCHOL_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    const size_t smem = (size_t)4 * n * sizeof(double);
+    const long long total = batch * (long long)nrhs;
+    const unsigned grid = (unsigned)std::min<long long>((total + 3) / 4, (long long)g_ctx[dev].sms * 16);
+    auto pu = reinterpret_cast<const unsigned long long*>(p);
+    if (mem_kind == MODCHOL_MEM_DEVICE) {
+        if (b == x) {
+            // x[p_i] = w_i is a scatter: an aliased rhs would be overwritten while still needed by
+            // another lane only within one system, and each system is staged in shared memory
+            // before any write -- aliasing is safe.
+        }
+        solve_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(batch, n, nrhs, l, pu, b, x);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+        return MODCHOL_OK;
+    }
+    if (mem_kind != MODCHOL_MEM_HOST)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown mem_kind %d", mem_kind);
+    const size_t nn = (size_t)n * n;
+    double *dl = nullptr, *db = nullptr;
+    unsigned long long* dp = nullptr;
+    cudaError_t ce = cudaMalloc(&dl, batch * nn * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&dp, (size_t)batch * n * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&db, (size_t)total * n * 8);
+    if (ce == cudaSuccess) ce = cudaMemcpy(dl, l, batch * nn * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(dp, p, (size_t)batch * n * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(db, b, (size_t)total * n * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        solve_kernel<<<grid, 128, smem>>>(batch, n, nrhs, dl, dp, db, db);
+        g_launches.fetch_add(1);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(x, db, (size_t)total * n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dl); cudaFree(dp); cudaFree(db);
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "solve: %s", cudaGetErrorString(ce));
+    return MODCHOL_OK;
+}
+
 }  // extern "C"

@@ -217,6 +217,31 @@ def test_edge_cases_propagate_like_the_reference(oracle, torch_cuda, mode):
                     assert rr <= 1e-12 * ls * ls, (algo, n, i, rr)
 
 
+@pytest.mark.parametrize("n", [1, 5, 32, 47, 130])
+def test_solve_batched_newton_step(torch_cuda, n):
+    """(A + E) x = b from {l, p}; checked against numpy on the host."""
+    rng = np.random.default_rng(n)
+    b = 40
+    # tiny n: PD inputs (a negative 1x1 makes SE90 return NaN, the reference's quirk at se90.rs:84)
+    a = matgen.make("wishart" if n >= 3 else "pd", 900 + n, b, n)
+    rhs = rng.standard_normal((b, 3, n))
+    for algo in ALGOS:
+        d = m.factor_batched(algo, a, mode="strict")
+        x = m.solve_batched(d, rhs)
+        xd = m.solve_batched(m.factor_batched(algo, torch_cuda.from_numpy(a).cuda()),
+                             torch_cuda.from_numpy(rhs).cuda()).cpu().numpy()
+        assert np.array_equal(x, xd)
+        for i in range(b):
+            ae = a[i] + np.diag(d.e[i])
+            ref = np.linalg.solve(ae, rhs[i].T).T
+            scale = np.abs(ref).max() * np.linalg.cond(ae)
+            assert np.abs(x[i] - ref).max() <= 1e-13 * scale + 1e-300, (algo, n, i)
+            res = np.abs(ae @ x[i].T - rhs[i].T).max()
+            assert res <= 1e-12 * np.abs(ae).max() * max(np.abs(x[i]).max(), 1.0) * n, (algo, n, i, res)
+    x1 = m.solve_batched(d, rhs[:, 0, :])
+    assert np.array_equal(x1, x[:, 0, :])
+
+
 def test_host_pointer_path_matches_device_path(oracle, torch_cuda):
     """numpy in -> the C-ABI stages through the GPU in overlapped chunks; results identical."""
     for algo, n, b in (("se99", 32, 5000), ("gmw81", 17, 3000), ("se90", 64, 700)):
