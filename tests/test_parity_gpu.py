@@ -262,6 +262,38 @@ def test_multi_gpu_entry_point_single_device(oracle, torch_cuda):
     assert np.array_equal(d1.l, d0.l) and np.array_equal(d1.e, d0.e) and np.array_equal(d1.p, d0.p)
 
 
+def test_eight_byte_aligned_buffers(oracle, torch_cuda):
+    """The C-ABI takes plain pointers: buffers that are only 8-byte aligned (a view one element
+    into an allocation) must work -- the register kernels then skip their 128-bit stores."""
+    import ctypes
+    from modcholesky_b200 import _lib
+    torch = torch_cuda
+    for algo, n, b in (("se99", 32, 300), ("se90", 16, 300), ("gmw81", 24, 200), ("se99", 64, 50)):
+        a = matgen.make("uniform", 70 + n, b, n)
+        ref = oracle.factor_batched(algo, a)
+        for mode in ("strict", "fast"):
+            pad_a = torch.empty(b * n * n + 1, dtype=torch.float64, device="cuda")
+            pad_l = torch.empty(b * n * n + 1, dtype=torch.float64, device="cuda")
+            pad_e = torch.empty(b * n + 1, dtype=torch.float64, device="cuda")
+            pad_p = torch.empty(b * n + 1, dtype=torch.int64, device="cuda")
+            av, lv, evv, pv = pad_a[1:], pad_l[1:], pad_e[1:], pad_p[1:]
+            assert lv.data_ptr() % 16 == 8
+            av.copy_(torch.from_numpy(a).reshape(-1))
+            rc = _lib.lib().modchol_factor_batched_f64(
+                _lib.algo_id(algo), _lib.mode_id(mode), b, n, av.data_ptr(), lv.data_ptr(), evv.data_ptr(),
+                pv.data_ptr(), None, _lib.MEM_DEVICE,
+                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.check(rc)
+            torch.cuda.synchronize()
+            l = lv.cpu().numpy().reshape(b, n, n)
+            p = pv.cpu().numpy().reshape(b, n).astype(np.uint64)
+            if mode == "strict":
+                assert np.array_equal(l, ref.l) and np.array_equal(p, ref.p), (algo, n)
+                assert np.array_equal(evv.cpu().numpy().reshape(b, n), ref.e), (algo, n)
+            else:
+                assert np.allclose(l, ref.l, rtol=1e-9, atol=1e-12), (algo, n)
+
+
 def test_input_is_never_written_and_empty_batch_ok(torch_cuda):
     torch = torch_cuda
     a = torch.from_numpy(matgen.make("uniform", 1, 64, 32)).cuda()
