@@ -287,9 +287,9 @@ def main():
     achieved = batch * ALG_BYTES / (ms_per_step * 1e-3) / 1e9      # per GPU: one launch per step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(),
-                "kernel": f"se_warp_kernel<SE99, NMAX=32, {args.mode}> (one launch per step)",
+                "kernel": f"{m.kernel_class(ALGO, N_MAT, args.mode)}: wsm_se_kernel<SE99, R=1, {args.mode}> (one launch per step)",
                 "algorithmic_bytes_per_matrix": ALG_BYTES, "peak_source": peak_src,
-                "note": "per-warp latency bound (7.4 cycles per issued instruction, 16 matrices per SM), not HBM bound: see profiles/r01_notes.md"}
+                "note": "instruction-issue bound (shared-memory-resident, left-looking), not HBM bound: see profiles/r01_notes.md"}
 
     line = {
         "metric": "matrices_per_sec", "value": value, "unit": "matrices/s", "n_gpus": world,

@@ -138,6 +138,25 @@ __device__ __forceinline__ double wsm_nd_sum_abs_col(const double* W, int lo, in
     return acc;
 }
 
+// ndarray-order sum of line[lo .. lo+len) (values already |.|), any len, returned to every lane:
+// lanes 0..7 own the eight partials, then the pairwise combine, then the tail.
+__device__ __forceinline__ double wsm_nd_sum_line(unsigned lineb, int lo, int len, int lane)
+{
+    const int nch = len >> 3;
+    double p = 0.0;
+    if (lane < 8)
+        for (int c = 0; c < nch; ++c)
+            p = dadd(p, lds_f64(lineb + 8u * (unsigned)(lo + 8 * c + lane)));
+    const double pair = dadd(p, __shfl_down_sync(kFull, p, 4));
+    double acc = dadd(0.0, __shfl_sync(kFull, pair, 0));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 1));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 2));
+    acc = dadd(acc, __shfl_sync(kFull, pair, 3));
+    for (int i = 8 * nch; i < len; ++i)
+        acc = dadd(acc, lds_f64(lineb + 8u * (unsigned)(lo + i)));
+    return acc;
+}
+
 // ndarray-order sum of |x[0 .. len)| with element t at W[base(t)], executed by ONE lane.
 template <typename AddrFn>
 __device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, AddrFn addr)
@@ -324,54 +343,75 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             }
             return fast;
         };
-        // E: write column j of L and update the trailing lower triangle
-        // (se90.rs:84-93 == :142-151, se99.rs:96-105 == :162-171)
+        // LEFT-looking evaluation of the pivot column.  The reference updates the whole trailing
+        // block at every step (l_ik -= l_ij l_kj, se90.rs:88-92); here columns >= j keep the
+        // permuted INPUT and column j is brought up to date only now:
+        //     col_i = a_ij - l_i,sbase l_j,sbase - ... - l_i,j-1 l_j,j-1      (in this order)
+        // which applies exactly the same roundings in the same order as the right-looking
+        // updates would have, with read-only shared-memory traffic (no store per element).
+        // sbase = first column not yet applied to the stored trailing block (0, or the phase-2
+        // start once the block has been materialised for the Gershgorin bounds).
+        auto left_column = [&](int j, unsigned tjb, int sbase, double (&col)[R]) {
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const bool mine = rv[s] && row[s] >= sbase && row[s] < j;
+                const double ljs = mine ? lds_f64(tjb + 8u * row[s]) : 0.0;   // row j of L
+                sts_f64_if(mine, lineb + 8u * row[s], ljs);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < R; ++s)
+                col[s] = lds_f64(tib[s] + 8u * j);
+            int t = sbase;
+            if ((t & 1) && t < j) {   // reach an even column so that the line reads are LDS.128
+                const double lj = lds_f64(lineb + 8u * t);
+#pragma unroll
+                for (int s = 0; s < R; ++s)
+                    col[s] = nmul_add<kStrict>(col[s], lds_f64(tib[s] + 8u * t), lj);
+                ++t;
+            }
+            for (; t + 4 <= j; t += 4) {
+                const double2 l01 = lds_v2f64(lineb + 8u * t);
+                const double2 l23 = lds_v2f64(lineb + 8u * t + 16);
+                const double lj[4] = {l01.x, l01.y, l23.x, l23.y};
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    double w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        w[u] = lds_f64(tib[s] + 8u * (t + u));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        col[s] = nmul_add<kStrict>(col[s], w[u], lj[u]);
+                }
+            }
+            for (; t < j; ++t) {
+                const double lj = lds_f64(lineb + 8u * t);
+#pragma unroll
+                for (int s = 0; s < R; ++s)
+                    col[s] = nmul_add<kStrict>(col[s], lds_f64(tib[s] + 8u * t), lj);
+            }
+#pragma unroll
+            for (int s = 0; s < R; ++s)
+                if (!(rv[s] && row[s] > j))
+                    col[s] = 0.0;
+            __syncwarp();
+        };
+        // write column j of L (se90.rs:84-87, se99.rs:96-99); the diagonal update of the
+        // reference's trailing update (l_ii -= l_ij^2) is carried in dg
         auto eliminate = [&](int j, unsigned tjb, double sq, const double (&cs)[R],
                              const double (&dg_new)[R]) {
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 const bool below = rv[s] && row[s] > j;
-                sts_f64_if(rv[s], lineb + 8u * row[s], cs[s]);
                 sts_f64_if(below || row[s] == j, below ? tib[s] + 8u * j : tjb + 8u * j,
                            below ? cs[s] : sq);
                 if (below)
                     dg[s] = dg_new[s];
             }
             __syncwarp();
-            // W(i,k) -= cs_i * cs_k for j < k <= i.  Four columns per trip; the first trip is
-            // aligned down to an even k so that the broadcast reads are LDS.128.  Loads and
-            // FMAs are unconditional (a lane may read past the end of its own row: still inside
-            // this warp's region); only the store is predicated on j < k <= row.
-            const int k0 = (j + 1) & ~1;
-            unsigned cnt[R], wr[R];
-#pragma unroll
-            for (int s = 0; s < R; ++s) {
-                const int c = rv[s] ? row[s] - j : 0;
-                cnt[s] = c > 0 ? (unsigned)c : 0u;          // columns j+1 .. row[s]
-                wr[s] = tib[s] + 8u * k0;
-            }
-            unsigned lk = lineb + 8u * k0;
-            for (int k = k0; k < n; k += 4) {
-                const double2 c01 = lds_v2f64(lk);
-                const double2 c23 = lds_v2f64(lk + 16);
-                const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
-                const unsigned off = (unsigned)(k - j - 1);  // wraps to UINT_MAX for k == j
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    double w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        w[u] = lds_f64(wr[s] + 8u * u);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        sts_f64_if(off + (unsigned)u < cnt[s], wr[s] + 8u * u,
-                                   nmul_add<kStrict>(w[u], cs[s], ck[u]));
-                    wr[s] += 32;
-                }
-                lk += 32;
-            }
-            __syncwarp();
         };
+        int sbase = 0;
 
         // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
         int j = 0;
@@ -393,6 +433,8 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             if (m != j)
                 swap_positions(j, m, tjb, false);
             const double piv = bcast_row(dg, j);
+            double colv[R];
+            left_column(j, tjb, sbase, colv);
             double sq, y, inv_piv;
             const bool fast = scale(piv, sq, y, inv_piv);
             double cs[R], dg_new[R], nv[R];
@@ -400,7 +442,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 below[s] = rv[s] && row[s] > j;
-                const double col = below[s] ? lds_f64(tib[s] + 8u * j) : 0.0;
+                const double col = colv[s];
                 cs[s] = fast ? dmul(col, y) : ddiv(col, sq);
                 dg_new[s] = nmul_add<kStrict>(dg[s], cs[s], cs[s]);
                 // look-ahead value (se90.rs:70-77, se99.rs:82-89); FAST: the updated diagonal
@@ -427,8 +469,57 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                         sts_f64(tib[s] + 8u * row[s], dsqrt(dadd(ljj, ej)));
                     }
             } else {
-                // lower Gershgorin bounds (se90.rs:105-110, se99.rs:125-130)
+                // The Gershgorin bounds need the whole trailing block as the reference holds it:
+                // apply the k0 finished columns to it once (same order, same roundings).
                 const int k0 = kstart;
+                if (k0 > sbase) {
+                    // one right-looking sweep per finished column t (in order): W(i,k) -= l_it l_kt
+                    // for k0 <= k <= i, four columns per trip, LDS.128 broadcasts of column t from
+                    // the line, unconditional load + FMA, predicated store
+                    const int kk0 = k0 & ~1;
+                    unsigned cnt[R];
+#pragma unroll
+                    for (int s = 0; s < R; ++s) {
+                        const int c = rv[s] ? row[s] - k0 + 1 : 0;
+                        cnt[s] = c > 0 ? (unsigned)c : 0u;      // columns k0 .. row[s]
+                    }
+                    for (int t = sbase; t < k0; ++t) {
+                        double lt[R];
+#pragma unroll
+                        for (int s = 0; s < R; ++s) {
+                            lt[s] = lds_f64(tib[s] + 8u * t);   // l_it (rows >= k0 > t)
+                            sts_f64_if(rv[s], lineb + 8u * row[s], lt[s]);
+                        }
+                        __syncwarp();
+                        unsigned wr[R];
+#pragma unroll
+                        for (int s = 0; s < R; ++s)
+                            wr[s] = tib[s] + 8u * kk0;
+                        unsigned lk = lineb + 8u * kk0;
+                        for (int k = kk0; k < n; k += 4) {
+                            const double2 c01 = lds_v2f64(lk);
+                            const double2 c23 = lds_v2f64(lk + 16);
+                            const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
+                            const unsigned off = (unsigned)(k - k0);   // wraps for k == k0 - 1
+#pragma unroll
+                            for (int s = 0; s < R; ++s) {
+                                double w[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    w[u] = lds_f64(wr[s] + 8u * u);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    sts_f64_if(off + (unsigned)u < cnt[s], wr[s] + 8u * u,
+                                               nmul_add<kStrict>(w[u], lt[s], ck[u]));
+                                wr[s] += 32;
+                            }
+                            lk += 32;
+                        }
+                        __syncwarp();
+                    }
+                    sbase = k0;
+                }
+                // lower Gershgorin bounds (se90.rs:105-110, se99.rs:125-130)
 #pragma unroll
                 for (int s = 0; s < R; ++s) {
                     const int i = row[s];
@@ -466,19 +557,25 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                     double col[R], acol[R];
                     bool below[R];
                     double part = 0.0;
+                    left_column(j, tjb, sbase, col);
 #pragma unroll
                     for (int s = 0; s < R; ++s) {
                         below[s] = rv[s] && row[s] > j;
-                        col[s] = below[s] ? lds_f64(tib[s] + 8u * j) : 0.0;
                         acol[s] = abs_bits(col[s]);
                         part = (s == 0) ? acol[s] : dadd(part, acol[s]);
                     }
                     // E_jj (se90.rs:124-131, se99.rs:144-151)
                     double normj;
-                    if constexpr (kStrict)
-                        normj = wsm_nd_sum_abs_col(W, j + 1, j, n - j - 1, lane);
-                    else
+                    if constexpr (kStrict) {
+#pragma unroll
+                        for (int s = 0; s < R; ++s)
+                            sts_f64_if(rv[s], lineb + 8u * row[s], acol[s]);
+                        __syncwarp();
+                        normj = wsm_nd_sum_line(lineb, j + 1, n - j - 1, lane);
+                        __syncwarp();
+                    } else {
                         normj = warp_sum_tree<32>(kFull, part);
+                    }
                     const double ej =
                         max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
                     if (kStrict) {
@@ -513,7 +610,9 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 double a00 = bcast_row(dg, n - 2);
                 double a11 = bcast_row(dg, n - 1);
                 const unsigned a10b = wb + 8u * (unsigned)(tri(n - 1) + n - 2);
-                double a10 = lds_f64(a10b);
+                double c2[R];
+                left_column(n - 2, wb + 8u * (unsigned)tri(n - 2), sbase, c2);
+                double a10 = bcast_row(c2, n - 1);
                 double lhi, llo;
                 eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);   // lower storage: m[0,1] == m[1,0]
                 const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);

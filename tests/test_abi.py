@@ -40,9 +40,10 @@ def test_version_and_kernel_classes():
     assert m.kernel_class("se99", 128) == "cta_packed" and m.kernel_class("se90", 236) == "cta_packed"
     assert m.kernel_class("se90", 237) == "cta_gmem" and m.kernel_class("gmw81", 128) == "cta_packed"
     assert m.kernel_class("se90", 64) == "warp_smem"
-    assert m.kernel_class("se99", 32, "fast") == "warp32" and m.kernel_class("gmw81", 64) == "warp_smem" and m.kernel_class("gmw81", 65) == "cta_packed"
+    assert m.kernel_class("se99", 32, "fast") == "warp_smem" and m.kernel_class("gmw81", 64) == "warp_smem"
+    assert m.kernel_class("gmw81", 65) == "cta_packed"
     assert m.kernel_class("se99", 32, "strict") == "warp_smem" and m.kernel_class("se99", 16, "strict") == "warp32"
-    assert m.kernel_class("gmw81", 32) == "warp32"
+    assert m.kernel_class("gmw81", 32) == "warp_smem" and m.kernel_class("gmw81", 16, "fast") == "warp32"
     assert m.kernel_class("se99", 4096) == "unsupported"
 
 
