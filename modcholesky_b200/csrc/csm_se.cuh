@@ -223,38 +223,50 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             }
             return fast;
         };
-        // column j of L + trailing lower-triangle update (se90.rs:84-93, se99.rs:96-105)
+        // LEFT-looking evaluation of the pivot column (see wsm_se.cuh): columns >= j keep the
+        // permuted input until column j is needed,
+        //     col_i = a_ij - l_i,sbase l_j,sbase - ... - l_i,j-1 l_j,j-1      (in this order),
+        // the same roundings in the same order as the reference's right-looking updates, with
+        // read-only shared-memory traffic.  Two __syncthreads (line fill, line release).
+        auto left_column = [&](int j, unsigned tjb, int sbase) -> double {
+            const bool mine = rv && row >= sbase && row < j;
+            const double ljs = mine ? lds_f64(tjb + 8u * row) : 0.0;   // row j of L
+            sts_f64_if(mine, lineb + 8u * row, ljs);
+            __syncthreads();
+            double col = lds_f64(tib + 8u * j);
+            int t = sbase;
+            if ((t & 1) && t < j) {
+                col = nmul_add<kStrict>(col, lds_f64(tib + 8u * t), lds_f64(lineb + 8u * t));
+                ++t;
+            }
+            for (; t + 4 <= j; t += 4) {
+                const double2 l01 = lds_v2f64(lineb + 8u * t);
+                const double2 l23 = lds_v2f64(lineb + 8u * t + 16);
+                const double lj[4] = {l01.x, l01.y, l23.x, l23.y};
+                double w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    w[u] = lds_f64(tib + 8u * (t + u));
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    col = nmul_add<kStrict>(col, w[u], lj[u]);
+            }
+            for (; t < j; ++t)
+                col = nmul_add<kStrict>(col, lds_f64(tib + 8u * t), lds_f64(lineb + 8u * t));
+            if (!(rv && row > j))
+                col = 0.0;
+            __syncthreads();
+            return col;
+        };
+        // write column j of L (se90.rs:84-87, se99.rs:96-99); the diagonal update is carried in dg
         auto eliminate = [&](int j, unsigned tjb, double sq, double cs, double dg_new) {
             const bool below = rv && row > j;
-            sts_f64_if(rv, lineb + 8u * row, cs);
             sts_f64_if(below || row == j, below ? tib + 8u * j : tjb + 8u * j, below ? cs : sq);
             if (below)
                 dg = dg_new;
             __syncthreads();
-            const int k0 = (j + 1) & ~1;
-            const int c = rv ? row - j : 0;
-            const unsigned cnt = c > 0 ? (unsigned)c : 0u;
-            unsigned wr = tib + 8u * k0, lk = lineb + 8u * k0;
-            // every thread only needs columns up to its own row: warps owning early rows
-            // finish early (the loop bound is warp-uniform: the largest row of the warp)
-            const int kend = min(n, (tid | 31) + 1);
-            for (int k = k0; k < kend; k += 4) {
-                const double2 c01 = lds_v2f64(lk);
-                const double2 c23 = lds_v2f64(lk + 16);
-                const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
-                const unsigned off = (unsigned)(k - j - 1);
-                double w[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    w[u] = lds_f64(wr + 8u * u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    sts_f64_if(off + (unsigned)u < cnt, wr + 8u * u, nmul_add<kStrict>(w[u], cs, ck[u]));
-                wr += 32;
-                lk += 32;
-            }
-            __syncthreads();
         };
+        int sbase = 0;
         // value of the row at position j, broadcast to the block (one sync)
         auto bcast_row = [&](double v, int j) -> double {
             double* D = sc.dbl + sc.buf * 8;
@@ -285,7 +297,7 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             double sq, y, inv_piv;
             const bool fast = scale(piv, sq, y, inv_piv);
             const bool below = rv && row > j;
-            const double col = below ? lds_f64(tib + 8u * j) : 0.0;
+            const double col = left_column(j, tjb, sbase);
             const double cs = fast ? dmul(col, y) : ddiv(col, sq);
             const double dg_new = nmul_add<kStrict>(dg, cs, cs);
             const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
@@ -308,7 +320,40 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                     sts_f64(tib + 8u * row, dsqrt(dadd(ljj, ej)));
                 }
             } else {
-                const int k0 = kstart;  // se90.rs:105-110, se99.rs:125-130
+                const int k0 = kstart;
+                if (k0 > sbase) {
+                    // materialise the trailing block for the Gershgorin bounds: one right-looking
+                    // sweep per finished column t, in order (same roundings as the reference)
+                    const int kk0 = k0 & ~1;
+                    const int c = rv ? row - k0 + 1 : 0;
+                    const unsigned cnt = c > 0 ? (unsigned)c : 0u;   // columns k0 .. row
+                    const int kend = min(n, (tid | 31) + 1);
+                    for (int t = sbase; t < k0; ++t) {
+                        const double lt = lds_f64(tib + 8u * t);
+                        sts_f64_if(rv, lineb + 8u * row, lt);
+                        __syncthreads();
+                        unsigned wr = tib + 8u * kk0, lk = lineb + 8u * kk0;
+                        for (int k = kk0; k < kend; k += 4) {
+                            const double2 c01 = lds_v2f64(lk);
+                            const double2 c23 = lds_v2f64(lk + 16);
+                            const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
+                            const unsigned off = (unsigned)(k - k0);
+                            double w[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                w[u] = lds_f64(wr + 8u * u);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                sts_f64_if(off + (unsigned)u < cnt, wr + 8u * u,
+                                           nmul_add<kStrict>(w[u], lt, ck[u]));
+                            wr += 32;
+                            lk += 32;
+                        }
+                        __syncthreads();
+                    }
+                    sbase = k0;
+                }
+                // se90.rs:105-110, se99.rs:125-130
                 if (rv && row >= k0) {
                     const int i = row, tis = tri(row);
                     if constexpr (kStrict) {
@@ -335,13 +380,15 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                         swap_positions(j, m, tjb);
                     double piv = bcast_row(dg, j);
                     const bool below = rv && row > j;
-                    const double col = below ? lds_f64(tib + 8u * j) : 0.0;
+                    const double col = left_column(j, tjb, sbase);
                     const double acol = abs_bits(col);
                     double normj;  // se90.rs:124, se99.rs:144
                     if constexpr (kStrict) {
+                        sts_f64_if(rv, lineb + 8u * row, acol);
+                        __syncthreads();
                         double* D = sc.dbl + sc.buf * 8;
                         if (tid < 32) {
-                            const double s = wsm_nd_sum_abs_col(W, j + 1, j, n - j - 1, lane);
+                            const double s = wsm_nd_sum_line(lineb, j + 1, n - j - 1, lane);
                             if (lane == 0)
                                 D[0] = s;
                         }
@@ -380,7 +427,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                 double a00 = bcast_row(dg, n - 2);
                 double a11 = bcast_row(dg, n - 1);
                 const unsigned a10b = wb + 8u * (unsigned)(tri(n - 1) + n - 2);
-                double a10 = lds_f64(a10b);
+                const double c2 = left_column(n - 2, wb + 8u * (unsigned)tri(n - 2), sbase);
+                double a10 = bcast_row(c2, n - 1);
                 double lhi, llo;
                 eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);
                 const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
