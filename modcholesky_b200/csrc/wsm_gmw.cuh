@@ -95,26 +95,7 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
         const double* Ab = A + (size_t)b * nn;
         // ---- load the lower triangle; off-diagonal maximum on the fly (gmw81.rs:52-58) --------
         __syncwarp();
-        double om = 0.0;
-        for (int i0 = 0; i0 < n; i0 += 8) {
-            double v[8][R];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int i = i0 + u, k = lane + 32 * s;
-                    v[u][s] = (i < n && k <= i) ? __ldg(Ab + i * n + k) : 0.0;
-                }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int i = i0 + u, k = lane + 32 * s;
-                    sts_f64_if(i < n && k <= i, wb + 8u * (unsigned)(tri(i) + k), v[u][s]);
-                    if (i < n && k < i)
-                        om = fmax(om, fabs(v[u][s]));
-                }
-        }
+        const double om = wsm_load_lower<R, true>(Ab, n, wb, lane);
         __syncwarp();
 
         double cd[R], ev[R], dpos[R], sqd[R], rdpos[R], av[R], omv[R], dummy[R];
@@ -221,17 +202,8 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
         }
 
         // ---- epilogue ---------------------------------------------------------------------
-        double* Lb = L + (size_t)b * nn;
-        for (int i0 = 0; i0 < n; i0 += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int i = i0 + u, k = lane + 32 * s;
-                    if (i < n && k < n)
-                        Lb[i * n + k] = (k <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + k)) : 0.0;
-                }
-        }
+        __syncwarp();
+        wsm_store_lower<R>(L + (size_t)b * nn, n, wb, lane);
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if (rv[s]) {

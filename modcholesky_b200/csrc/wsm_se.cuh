@@ -40,6 +40,8 @@ template <bool kMax, int R>
 __device__ __forceinline__ double wsm_extreme(const double (&v)[R], const bool (&cand)[R], double none,
                                               bool (&win)[R])
 {
+    if constexpr (R == 1)
+        return warp_extreme<kMax>(kFull, v[0], cand[0], none, win[0]);
     int khi[R];
     unsigned klo[R];
     bool c[R];
@@ -74,6 +76,8 @@ template <int R>
 __device__ __forceinline__ int wsm_argmax_first(const double (&v)[R], const bool (&active)[R],
                                                 const int (&row)[R], int lo, double& best)
 {
+    if constexpr (R == 1)
+        return warp_argmax_first(kFull, v[0], active[0], row[0], lo, best);
     bool win[R];
     best = wsm_extreme<true, R>(v, active, -INFINITY, win);
     unsigned mine = 1024u;
@@ -113,6 +117,95 @@ __device__ __forceinline__ void sts_f64_if(bool pred, unsigned a, double v)
 {
     asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}"
                  :: "r"(a), "d"(v), "r"((int)pred) : "memory");
+}
+
+// ld.shared.f64 where pred, else 0.0 -- one predicated load into a zeroed register
+__device__ __forceinline__ double lds_f64_or_zero(bool pred, unsigned a)
+{
+    double v;
+    asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n mov.f64 %0, 0d0000000000000000;\n"
+                 " @q ld.shared.f64 %0, [%1];\n}"
+                 : "=d"(v) : "r"(a), "r"((int)pred) : "memory");
+    return v;
+}
+
+// Epilogue shared by the shared-memory warp kernels: the packed lower triangle at byte address wb
+// goes out as a dense row-major n x n matrix with an explicitly zero strict upper triangle
+// (se99.rs:189-192); lane = column, one coalesced row per store, running addresses.
+template <int R>
+__device__ __forceinline__ void wsm_store_lower(double* __restrict__ Lb, int n, unsigned wb, int lane)
+{
+    double* dst[R];
+    unsigned src[R];
+    bool kv[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        dst[s] = Lb + lane + 32 * s;
+        src[s] = wb + 8u * (unsigned)(lane + 32 * s);
+        kv[s] = lane + 32 * s < n;
+    }
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const double v = lds_f64_or_zero(kv[s] && lane + 32 * s <= i, src[s]);
+            if (kv[s])
+                *dst[s] = v;
+            dst[s] += n;
+            src[s] += 8u * (unsigned)(i + 1);
+        }
+    }
+}
+
+// Prologue shared by the shared-memory warp kernels: the lower triangle of the dense row-major
+// input goes into the packed triangle at byte address wb (lane = column, eight rows of loads in
+// flight per trip, running addresses).  kOffMax: also return this lane's max |a_ik|, k < i
+// (gmw81.rs:52-58; A symmetric, so the lower off-diagonals carry the off-diagonal maximum).
+template <int R, bool kOffMax>
+__device__ __forceinline__ double wsm_load_lower(const double* __restrict__ Ab, int n, unsigned wb, int lane)
+{
+    const double* src[R];
+    unsigned dst[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        src[s] = Ab + lane + 32 * s;
+        dst[s] = wb + 8u * (unsigned)(lane + 32 * s);
+    }
+    double om = 0.0;
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double v[8][R];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int s = 0; s < R; ++s)
+                v[u][s] = (lane + 32 * s <= i + u) ? __ldg(src[s] + (size_t)u * n) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                sts_f64_if(lane + 32 * s <= i + u, dst[s], v[u][s]);
+                dst[s] += 8u * (unsigned)(i + u + 1);
+                if (kOffMax)
+                    om = fmax(om, (lane + 32 * s == i + u) ? 0.0 : fabs(v[u][s]));
+            }
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            src[s] += (size_t)8 * n;
+    }
+    for (; i < n; ++i) {
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const bool in = lane + 32 * s <= i;
+            const double v = in ? __ldg(src[s]) : 0.0;
+            sts_f64_if(in, dst[s], v);
+            dst[s] += 8u * (unsigned)(i + 1);
+            src[s] += n;
+            if (kOffMax)
+                om = fmax(om, (lane + 32 * s == i) ? 0.0 : fabs(v));
+        }
+    }
+    return om;
 }
 
 // ndarray-order sum of |W(lo + t, col)|, t = 0 .. len-1 (a column below the diagonal), any len:
@@ -287,23 +380,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         const double* Ab = A + (size_t)b * nn;
         // ---- load the lower triangle, eight rows per trip (coalesced, loads batched) --------
         __syncwarp();
-        for (int i0 = 0; i0 < n; i0 += 8) {
-            double v[8][R];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int i = i0 + u, k = lane + 32 * s;
-                    v[u][s] = (i < n && k <= i) ? __ldg(Ab + i * n + k) : 0.0;
-                }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int i = i0 + u, k = lane + 32 * s;
-                    sts_f64_if(i < n && k <= i, wb + 8u * (unsigned)(tri(i) + k), v[u][s]);
-                }
-        }
+        wsm_load_lower<R, false>(Ab, n, wb, lane);
         __syncwarp();
 
         double dg[R], g[R], ev[R];
@@ -352,50 +429,74 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         // sbase = first column not yet applied to the stored trailing block (0, or the phase-2
         // start once the block has been materialised for the Gershgorin bounds).
         auto left_column = [&](int j, unsigned tjb, int sbase, double (&col)[R]) {
-#pragma unroll
-            for (int s = 0; s < R; ++s) {
-                const bool mine = rv[s] && row[s] >= sbase && row[s] < j;
-                const double ljs = mine ? lds_f64(tjb + 8u * row[s]) : 0.0;   // row j of L
-                sts_f64_if(mine, lineb + 8u * row[s], ljs);
-            }
-            __syncwarp();
+            // row j of L is contiguous at tjb (W(j, 0..j-1)) and is read by warp-wide broadcast
+            // loads, two columns per LDS.128 once (tjb + 8 t) is 16-byte aligned
 #pragma unroll
             for (int s = 0; s < R; ++s)
                 col[s] = lds_f64(tib[s] + 8u * j);
-            int t = sbase;
-            if ((t & 1) && t < j) {   // reach an even column so that the line reads are LDS.128
-                const double lj = lds_f64(lineb + 8u * t);
+            unsigned rj = tjb + 8u * (unsigned)sbase;
+            unsigned ri[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s)
+                ri[s] = tib[s] + 8u * (unsigned)sbase;
+            int left = j - sbase;
+            auto step1 = [&]() {
+                const double lj = lds_f64(rj);
 #pragma unroll
                 for (int s = 0; s < R; ++s)
-                    col[s] = nmul_add<kStrict>(col[s], lds_f64(tib[s] + 8u * t), lj);
-                ++t;
-            }
-            for (; t + 4 <= j; t += 4) {
-                const double2 l01 = lds_v2f64(lineb + 8u * t);
-                const double2 l23 = lds_v2f64(lineb + 8u * t + 16);
-                const double lj[4] = {l01.x, l01.y, l23.x, l23.y};
+                    col[s] = nmul_add<kStrict>(col[s], lds_f64(ri[s]), lj);
+            };
+            auto step2 = [&](unsigned o) {
+                const double2 l01 = lds_v2f64(rj + o);
 #pragma unroll
                 for (int s = 0; s < R; ++s) {
-                    double w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        w[u] = lds_f64(tib[s] + 8u * (t + u));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        col[s] = nmul_add<kStrict>(col[s], w[u], lj[u]);
+                    const double w0 = lds_f64(ri[s] + o), w1 = lds_f64(ri[s] + o + 8);
+                    col[s] = nmul_add<kStrict>(col[s], w0, l01.x);
+                    col[s] = nmul_add<kStrict>(col[s], w1, l01.y);
                 }
-            }
-            for (; t < j; ++t) {
-                const double lj = lds_f64(lineb + 8u * t);
+            };
+            auto advance = [&](unsigned bytes) {
+                rj += bytes;
 #pragma unroll
                 for (int s = 0; s < R; ++s)
-                    col[s] = nmul_add<kStrict>(col[s], lds_f64(tib[s] + 8u * t), lj);
+                    ri[s] += bytes;
+            };
+            if ((rj & 8u) && left > 0) {
+                step1();
+                advance(8);
+                --left;
             }
+            for (; left >= 8; left -= 8) {
+                const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
+                const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
+                const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    double w[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        w[u] = lds_f64(ri[s] + 8u * u);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        col[s] = nmul_add<kStrict>(col[s], w[u], lj[u]);
+                }
+                advance(64);
+            }
+            if (left & 4) {
+                step2(0);
+                step2(16);
+                advance(32);
+            }
+            if (left & 2) {
+                step2(0);
+                advance(16);
+            }
+            if (left & 1)
+                step1();
 #pragma unroll
             for (int s = 0; s < R; ++s)
                 if (!(rv[s] && row[s] > j))
                     col[s] = 0.0;
-            __syncwarp();
         };
         // write column j of L (se90.rs:84-87, se99.rs:96-99); the diagonal update of the
         // reference's trailing update (l_ii -= l_ij^2) is carried in dg
@@ -641,17 +742,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         __syncwarp();
 
         // ---- epilogue: L (strict upper explicitly zero), e un-permuted, p -------------------
-        double* Lb = L + (size_t)b * nn;
-        for (int i0 = 0; i0 < n; i0 += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const int i = i0 + u, k = lane + 32 * s;
-                    if (i < n && k < n)
-                        Lb[i * n + k] = (k <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + k)) : 0.0;
-                }
-        }
+        wsm_store_lower<R>(L + (size_t)b * nn, n, wb, lane);
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if (rv[s]) {
