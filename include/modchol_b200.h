@@ -120,9 +120,9 @@ int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const doub
  * "cta_smem", "cta_gmem" -- for logging and tests.  Never NULL. */
 const char *modchol_kernel_class(int algo, int mode, int32_t n);
 
-/* Tuning knob: which small-n kernel family serves n <= 32 -- 0 = automatic (register-resident
- * "warp32" for n <= 16, shared-memory-resident "warp_smem" for 16 < n <= 32), 1 =
- * register-resident, 2 = shared-memory-resident ("warp_smem" always serves 32 < n <= 64).
+/* Tuning knob: which small-n kernel family serves n <= 32 -- 0 = automatic (the
+ * shared-memory-resident "warp_smem" family), 1 = register-resident "warp32", 2 =
+ * shared-memory-resident ("warp_smem" always serves 32 < n <= 64).
  * Returns the previous setting.  Both families produce identical STRICT results; the knob
  * exists for benchmarking and tests. */
 int modchol_set_small_kernel_family(int family);

@@ -144,11 +144,11 @@ KernelClass classify(int algo, int mode, int n, int smem_optin)
     const bool reg_ok = warp_kernel_available(algo, mode, n);
     const bool wsm_ok = wsm_kernel_available(algo, mode, n);
     const int pref = small_kernel_pref();
-    // Measured: the register family wins for n <= 16 (several matrices per
-    // warp); from n = 17 the shared-memory family (left-looking, 32 warps per SM) is at least as
-    // fast in both modes (SE99 n = 32 FAST: 80 vs 74 M/s, STRICT: 52 vs 22..50 M/s) and it is
-    // the only warp-level kernel for 32 < n <= 64.
-    const bool auto_wsm = wsm_ok && (!reg_ok || n > 16);
+    // Measured: the shared-memory family (left-looking, 32 warps per SM,
+    // 32/16/8/4 lanes per matrix) is at least as fast as the register family at every n in both
+    // modes for all but a few (n <= 8, STRICT, mixed-phase) cases, and it is the only warp-level
+    // kernel for 32 < n <= 64 -- it is the default; the register family stays selectable.
+    const bool auto_wsm = wsm_ok;
     if (wsm_ok && (pref == 2 || (pref == 0 && auto_wsm) || !reg_ok))
         return kClsWarpSmem;
     if (reg_ok)

@@ -66,37 +66,40 @@ __device__ __forceinline__ double wsm_gmw_dot(unsigned lineb, unsigned rowb, int
     }
 }
 
-template <int R, bool kStrict, int kWarps, int kMinBlocks>
+template <int G, int R, bool kStrict, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
                int* __restrict__ K)
 {
     extern __shared__ double sm[];
+    constexpr int kPack = 32 / G;   // matrices per warp, G lanes each (see wsm_se.cuh)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* W = sm + (size_t)wib * wstride;
+    const int sub = lane & (G - 1), grp = lane / G;
+    const unsigned mask = wsm_group_mask<G>(grp);
+    double* W = sm + (size_t)(wib * kPack + grp) * wstride;
     const unsigned wb = (unsigned)__cvta_generic_to_shared(W);
     const unsigned scrb = wb + 8u * (unsigned)((tri(n) + 1) & ~1);
     const unsigned lineb = scrb + 128u;
     const size_t nn = (size_t)n * n;
-    const long long nwarps = (long long)gridDim.x * kWarps;
+    const long long nslots = (long long)gridDim.x * kWarps * kPack;
 
     int row[R];
     unsigned tib[R];
     bool rv[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        row[s] = lane + 32 * s;
+        row[s] = sub + G * s;
         rv[s] = row[s] < n;
         tib[s] = wb + 8u * (unsigned)tri(rv[s] ? row[s] : 0);
     }
 
-    for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nwarps) {
+    for (long long b = ((long long)blockIdx.x * kWarps + wib) * kPack + grp; b < batch; b += nslots) {
         const double* Ab = A + (size_t)b * nn;
         // ---- load the lower triangle; off-diagonal maximum on the fly (gmw81.rs:52-58) --------
-        __syncwarp();
-        const double om = wsm_load_lower<R, true>(Ab, n, wb, lane);
-        __syncwarp();
+        __syncwarp(mask);
+        const double om = wsm_load_lower<G, R, true>(Ab, n, wb, sub);
+        __syncwarp(mask);
 
         double cd[R], ev[R], dpos[R], sqd[R], rdpos[R], av[R], omv[R], dummy[R];
         int perm[R];
@@ -116,8 +119,8 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
         for (int s = 0; s < R; ++s)
             all[s] = s == 0;
         // gmw81.rs:49-64 (A symmetric: the lower off-diagonals carry the off-diagonal maximum)
-        const double diag_max = wsm_extreme<true, R>(av, rv, 0.0, win);
-        const double off_max = wsm_extreme<true, R>(omv, all, 0.0, win);
+        const double diag_max = wsm_extreme<true, R>(mask, av, rv, 0.0, win);
+        const double off_max = wsm_extreme<true, R>(mask, omv, all, 0.0, win);
         const double nf = (double)n;
         const double delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(diag_max, off_max)));
         const double beta =
@@ -134,9 +137,9 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
                 av[s] = fabs(cd[s]);
             }
             double best;
-            const int m = wsm_argmax_first<R>(av, active, row, j, best);
+            const int m = wsm_argmax_first<R>(mask, av, active, row, j, best);
             if (m != j)
-                wsm_swap_positions<R>(wb, scrb, tib, row, rv, lane, j, m, tjb, cd, dummy, perm);
+                wsm_swap_positions<G, R>(mask, wb, scrb, tib, row, rv, sub, j, m, tjb, cd, dummy, perm);
             // ---- l_js = c_js / d_s, s < j (gmw81.rs:79-81): lane s owns d_s -----------------
             double ljs[R];
 #pragma unroll
@@ -148,7 +151,7 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
                     sts_f64(lineb + 8u * row[s], ljs[s]);
                 }
             }
-            __syncwarp();
+            __syncwarp(mask);
             // ---- c_ij = l_ij - sum_s l_js c_is for i >= j (gmw81.rs:83-85) ------------------
             double cij[R], acij[R];
             bool below[R];
@@ -163,8 +166,8 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
                 acij[s] = fabs(cij[s]);
             }
             // theta = max_{i>j} |c_ij|, 0 for the last column (gmw81.rs:87-100)
-            const double theta = wsm_extreme<true, R>(acij, below, 0.0, win);
-            const double cjj = wsm_bcast_row<R>(cij, j);
+            const double theta = wsm_extreme<true, R>(mask, acij, below, 0.0, win);
+            const double cjj = wsm_bcast_row<G, R>(mask, cij, j);
             const double tb = kStrict ? ddiv(theta, beta) : dmul(theta, rbeta);
             const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
             double sq, rdj = 0.0;
@@ -178,7 +181,7 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
                 if (!kStrict)
                     rdj = ddiv(1.0, dj);
             }
-            __syncwarp();   // row j's lane has read its c_js (dot product) before they are replaced
+            __syncwarp(mask);   // row j's lane has read its c_js (dot product) before they are replaced
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 // row j is final from here on: L_js = l_js * sqrt(d_s); the reference's dense dot
@@ -198,19 +201,19 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
                     rdpos[s] = rdj;
                 }
             }
-            __syncwarp();
+            __syncwarp(mask);
         }
 
         // ---- epilogue ---------------------------------------------------------------------
-        __syncwarp();
-        wsm_store_lower<R>(L + (size_t)b * nn, n, wb, lane);
+        __syncwarp(mask);
+        wsm_store_lower<G, R>(L + (size_t)b * nn, n, wb, sub);
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if (rv[s]) {
                 E[(size_t)b * n + perm[s]] = ev[s];                          // gmw81.rs:127-131
                 P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
             }
-        if (K && lane == 0)
+        if (K && sub == 0)
             K[b] = -1;
     }
 }

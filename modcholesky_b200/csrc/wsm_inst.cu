@@ -1,5 +1,7 @@
 // wsm_inst.cu -- instantiates the shared-memory-resident warp kernels (wsm_se.cuh) for ONE
 // (algorithm, mode) pair: -DMODCHOL_INST_ALGO={1,2} -DMODCHOL_INST_STRICT={0,1}.
+#include <cstdlib>
+
 #include "warp_kernels.cuh"
 #include "wsm_gmw.cuh"
 #include "wsm_se.cuh"
@@ -7,26 +9,32 @@
 #ifndef MODCHOL_WSM_MINB
 #define MODCHOL_WSM_MINB 8   /* resident 4-warp blocks per SM asked of ptxas for n <= 32 */
 #endif
+#ifndef MODCHOL_WSM_MINB_PACKED
+#define MODCHOL_WSM_MINB_PACKED 6   /* same, two matrices per warp with two rows per lane */
+#endif
 #ifndef MODCHOL_INST_ALGO
 #error "compile with -DMODCHOL_INST_ALGO=.. -DMODCHOL_INST_STRICT=.."
 #endif
 
 namespace modchol {
 
-template <int kAlgo, int R, bool kStrict>
+template <int kAlgo, int G, int R, bool kStrict>
 static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
     constexpr int kWarps = 4;
-    constexpr int kMinBlocks = R == 1 ? MODCHOL_WSM_MINB : 3;
+    constexpr int kPack = 32 / G;   // matrices per warp
+    // resident 4-warp blocks asked of ptxas: one matrix per warp and one row per lane fits 64
+    // registers (8 blocks); two rows per lane wants ~80 (6 blocks packed, 3 at n <= 64)
+    constexpr int kMinBlocks = R == 1 ? MODCHOL_WSM_MINB : (G == 16 ? MODCHOL_WSM_MINB_PACKED : 3);
     auto kern = [] {
         if constexpr (kAlgo == kGMW81)
-            return wsm_gmw_kernel<R, kStrict, kWarps, kMinBlocks>;
+            return wsm_gmw_kernel<G, R, kStrict, kWarps, kMinBlocks>;
         else
-            return wsm_se_kernel<kAlgo, R, kStrict, kWarps, kMinBlocks>;
+            return wsm_se_kernel<kAlgo, G, R, kStrict, kWarps, kMinBlocks>;
     }();
     const int wstride = wsm_warp_doubles(n);
-    const size_t smem = (size_t)kWarps * wstride * sizeof(double);
+    const size_t smem = (size_t)kWarps * kPack * wstride * sizeof(double);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
     // the matrices live in shared memory: ask for the largest shared-memory carve-out
@@ -37,11 +45,21 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem);
     if (ce != cudaSuccess) return ce;
     if (occ < 1) occ = 1;
-    long long blocks = (batch + kWarps - 1) / kWarps;
+    long long blocks = (batch + kWarps * kPack - 1) / (kWarps * kPack);
     const long long resident = (long long)sms * occ;
-    if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
+    if (blocks > resident) blocks = resident;   // persistent: every lane group strides over the batch
     kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(n, wstride, batch, a, l, e, p, k);
     return cudaGetLastError();
+}
+
+// 16 < n <= 32 can also run two matrices per warp (16 lanes x 2 rows each): 11 % fewer
+// instructions per matrix and +4 % (FAST) / +20 % (STRICT) when every matrix takes the same
+// path, but -27 % when the two matrices of a warp leave phase 1 at different columns and the
+// halves serialise (profiles/r01_notes.md) -- opt-in with MODCHOL_WSM_PACK=1, read per call.
+static bool wsm_pack_pref()
+{
+    const char* v = getenv("MODCHOL_WSM_PACK");
+    return v && v[0] == '1';
 }
 
 #define MODCHOL_CAT2(a, b, c, d) a##b##c##d
@@ -52,9 +70,16 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
 {
     constexpr int A = MODCHOL_INST_ALGO;
     constexpr bool S = MODCHOL_INST_STRICT != 0;
+    if (n <= 4)
+        return launch_wsm<A, 4, 1, S>(n, batch, a, l, e, p, k, sms, st);
+    if (n <= 8)
+        return launch_wsm<A, 8, 1, S>(n, batch, a, l, e, p, k, sms, st);
+    if (n <= 16)
+        return launch_wsm<A, 16, 1, S>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 32)
-        return launch_wsm<A, 1, S>(n, batch, a, l, e, p, k, sms, st);
-    return launch_wsm<A, 2, S>(n, batch, a, l, e, p, k, sms, st);
+        return wsm_pack_pref() ? launch_wsm<A, 16, 2, S>(n, batch, a, l, e, p, k, sms, st)
+                               : launch_wsm<A, 32, 1, S>(n, batch, a, l, e, p, k, sms, st);
+    return launch_wsm<A, 32, 2, S>(n, batch, a, l, e, p, k, sms, st);
 }
 
 }  // namespace modchol

@@ -31,17 +31,26 @@ __device__ __forceinline__ void st_shared_if(bool pred, double* p, double v)
                  :: "r"(a), "d"(v), "r"((int)pred) : "memory");
 }
 
-// doubles of shared memory per warp: packed triangle + 16 scratch + a 64-entry column line,
-// kept 16-byte aligned
-__host__ __device__ inline int wsm_warp_doubles(int n) { return ((tri(n) + 1) & ~1) + 16 + 72; }
+// doubles of shared memory per matrix: packed triangle + 16 scratch + a column line of n entries
+// (+8: the catch-up sweep reads it four at a time), kept 16-byte aligned
+__host__ __device__ inline int wsm_warp_doubles(int n)
+{
+    const int d = ((tri(n) + 1) & ~1) + 16 + ((n + 9) & ~1);
+    // n <= 8: four matrices per warp, two per shared-memory wavefront -- a stride of 8 (mod 16)
+    // doubles puts the second matrix on the banks the first one leaves free; n <= 4: eight per
+    // warp, four per wavefront, stride 4 (mod 16): T(0..3) = {0,1,3,6} + {0,4,8,12} are distinct
+    if (n <= 4)
+        return ((d + 11) & ~15) + 4;
+    return n <= 8 ? ((d + 7) & ~15) + 8 : d;
+}
 
 // local (per lane, over its R rows) then warp-wide extreme of v over candidate rows.
 template <bool kMax, int R>
-__device__ __forceinline__ double wsm_extreme(const double (&v)[R], const bool (&cand)[R], double none,
-                                              bool (&win)[R])
+__device__ __forceinline__ double wsm_extreme(unsigned mask, const double (&v)[R], const bool (&cand)[R],
+                                              double none, bool (&win)[R])
 {
     if constexpr (R == 1)
-        return warp_extreme<kMax>(kFull, v[0], cand[0], none, win[0]);
+        return warp_extreme<kMax>(mask, v[0], cand[0], none, win[0]);
     int khi[R];
     unsigned klo[R];
     bool c[R];
@@ -61,8 +70,8 @@ __device__ __forceinline__ double wsm_extreme(const double (&v)[R], const bool (
         }
     }
     const int INT_MIN_ = (int)0x80000000;
-    const int mh = __reduce_max_sync(kFull, bh);
-    const unsigned ml = __reduce_max_sync(kFull, bh == mh ? bl : 0u);
+    const int mh = __reduce_max_sync(mask, bh);
+    const unsigned ml = __reduce_max_sync(mask, bh == mh ? bl : 0u);
 #pragma unroll
     for (int s = 0; s < R; ++s)
         win[s] = c[s] && khi[s] == mh && klo[s] == ml;
@@ -73,13 +82,14 @@ __device__ __forceinline__ double wsm_extreme(const double (&v)[R], const bool (
 
 // first-strict-maximum pivot search over rows [lo, n) (utils.rs:52-91): position of the winner
 template <int R>
-__device__ __forceinline__ int wsm_argmax_first(const double (&v)[R], const bool (&active)[R],
-                                                const int (&row)[R], int lo, double& best)
+__device__ __forceinline__ int wsm_argmax_first(unsigned mask, const double (&v)[R],
+                                                const bool (&active)[R], const int (&row)[R], int lo,
+                                                double& best)
 {
     if constexpr (R == 1)
-        return warp_argmax_first(kFull, v[0], active[0], row[0], lo, best);
+        return warp_argmax_first(mask, v[0], active[0], row[0], lo, best);
     bool win[R];
-    best = wsm_extreme<true, R>(v, active, -INFINITY, win);
+    best = wsm_extreme<true, R>(mask, v, active, -INFINITY, win);
     unsigned mine = 1024u;
     bool head_nan = false;
 #pragma unroll
@@ -88,8 +98,8 @@ __device__ __forceinline__ int wsm_argmax_first(const double (&v)[R], const bool
             mine = (unsigned)row[s];
         head_nan = head_nan || (active[s] && row[s] == lo && (v[s] != v[s]));
     }
-    int m = (int)__reduce_min_sync(kFull, mine);
-    if (__any_sync(kFull, head_nan) || m > 255)
+    int m = (int)__reduce_min_sync(mask, mine);
+    if (__any_sync(mask, head_nan) || m > 255)
         m = lo;
     return m;
 }
@@ -132,23 +142,23 @@ __device__ __forceinline__ double lds_f64_or_zero(bool pred, unsigned a)
 // Epilogue shared by the shared-memory warp kernels: the packed lower triangle at byte address wb
 // goes out as a dense row-major n x n matrix with an explicitly zero strict upper triangle
 // (se99.rs:189-192); lane = column, one coalesced row per store, running addresses.
-template <int R>
-__device__ __forceinline__ void wsm_store_lower(double* __restrict__ Lb, int n, unsigned wb, int lane)
+template <int G, int R>
+__device__ __forceinline__ void wsm_store_lower(double* __restrict__ Lb, int n, unsigned wb, int sub)
 {
     double* dst[R];
     unsigned src[R];
     bool kv[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        dst[s] = Lb + lane + 32 * s;
-        src[s] = wb + 8u * (unsigned)(lane + 32 * s);
-        kv[s] = lane + 32 * s < n;
+        dst[s] = Lb + sub + G * s;
+        src[s] = wb + 8u * (unsigned)(sub + G * s);
+        kv[s] = sub + G * s < n;
     }
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            const double v = lds_f64_or_zero(kv[s] && lane + 32 * s <= i, src[s]);
+            const double v = lds_f64_or_zero(kv[s] && sub + G * s <= i, src[s]);
             if (kv[s])
                 *dst[s] = v;
             dst[s] += n;
@@ -161,15 +171,15 @@ __device__ __forceinline__ void wsm_store_lower(double* __restrict__ Lb, int n, 
 // input goes into the packed triangle at byte address wb (lane = column, eight rows of loads in
 // flight per trip, running addresses).  kOffMax: also return this lane's max |a_ik|, k < i
 // (gmw81.rs:52-58; A symmetric, so the lower off-diagonals carry the off-diagonal maximum).
-template <int R, bool kOffMax>
-__device__ __forceinline__ double wsm_load_lower(const double* __restrict__ Ab, int n, unsigned wb, int lane)
+template <int G, int R, bool kOffMax>
+__device__ __forceinline__ double wsm_load_lower(const double* __restrict__ Ab, int n, unsigned wb, int sub)
 {
     const double* src[R];
     unsigned dst[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        src[s] = Ab + lane + 32 * s;
-        dst[s] = wb + 8u * (unsigned)(lane + 32 * s);
+        src[s] = Ab + sub + G * s;
+        dst[s] = wb + 8u * (unsigned)(sub + G * s);
     }
     double om = 0.0;
     int i = 0;
@@ -179,15 +189,15 @@ __device__ __forceinline__ double wsm_load_lower(const double* __restrict__ Ab, 
         for (int u = 0; u < 8; ++u)
 #pragma unroll
             for (int s = 0; s < R; ++s)
-                v[u][s] = (lane + 32 * s <= i + u) ? __ldg(src[s] + (size_t)u * n) : 0.0;
+                v[u][s] = (sub + G * s <= i + u) ? __ldg(src[s] + (size_t)u * n) : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                sts_f64_if(lane + 32 * s <= i + u, dst[s], v[u][s]);
+                sts_f64_if(sub + G * s <= i + u, dst[s], v[u][s]);
                 dst[s] += 8u * (unsigned)(i + u + 1);
                 if (kOffMax)
-                    om = fmax(om, (lane + 32 * s == i + u) ? 0.0 : fabs(v[u][s]));
+                    om = fmax(om, (sub + G * s == i + u) ? 0.0 : fabs(v[u][s]));
             }
 #pragma unroll
         for (int s = 0; s < R; ++s)
@@ -196,58 +206,41 @@ __device__ __forceinline__ double wsm_load_lower(const double* __restrict__ Ab, 
     for (; i < n; ++i) {
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            const bool in = lane + 32 * s <= i;
+            const bool in = sub + G * s <= i;
             const double v = in ? __ldg(src[s]) : 0.0;
             sts_f64_if(in, dst[s], v);
             dst[s] += 8u * (unsigned)(i + 1);
             src[s] += n;
             if (kOffMax)
-                om = fmax(om, (lane + 32 * s == i) ? 0.0 : fabs(v));
+                om = fmax(om, (sub + G * s == i) ? 0.0 : fabs(v));
         }
     }
     return om;
 }
 
-// ndarray-order sum of |W(lo + t, col)|, t = 0 .. len-1 (a column below the diagonal), any len:
-// lanes 0..7 own the eight partials, then ((0+(p0+p4))+(p1+p5))+(p2+p6))+(p3+p7), then the tail.
-__device__ __forceinline__ double wsm_nd_sum_abs_col(const double* W, int lo, int col, int len, int lane)
-{
-    const int nch = len >> 3;
-    double p = 0.0;
-    if (lane < 8)
-        for (int c = 0; c < nch; ++c) {
-            const int r = lo + 8 * c + lane;
-            p = dadd(p, fabs(W[tri(r) + col]));
-        }
-    const double pair = dadd(p, __shfl_down_sync(kFull, p, 4));
-    double acc = dadd(0.0, __shfl_sync(kFull, pair, 0));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 1));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 2));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 3));
-    for (int i = 8 * nch; i < len; ++i) {
-        const int r = lo + i;
-        acc = dadd(acc, fabs(W[tri(r) + col]));
-    }
-    return acc;
-}
-
 // ndarray-order sum of line[lo .. lo+len) (values already |.|), any len, returned to every lane:
 // lanes 0..7 own the eight partials, then the pairwise combine, then the tail.
-__device__ __forceinline__ double wsm_nd_sum_line(unsigned lineb, int lo, int len, int lane)
+template <int G>
+__device__ __forceinline__ double wsm_nd_sum_line(unsigned mask, unsigned lineb, int lo, int len, int sub)
 {
     const int nch = len >> 3;
     double p = 0.0;
-    if (lane < 8)
+    if (sub < 8)
         for (int c = 0; c < nch; ++c)
-            p = dadd(p, lds_f64(lineb + 8u * (unsigned)(lo + 8 * c + lane)));
-    const double pair = dadd(p, __shfl_down_sync(kFull, p, 4));
-    double acc = dadd(0.0, __shfl_sync(kFull, pair, 0));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 1));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 2));
-    acc = dadd(acc, __shfl_sync(kFull, pair, 3));
+            p = dadd(p, lds_f64(lineb + 8u * (unsigned)(lo + 8 * c + sub)));
+    const double pair = dadd(p, __shfl_down_sync(mask, p, 4, G));
+    double acc = dadd(0.0, __shfl_sync(mask, pair, 0, G));
+    acc = dadd(acc, __shfl_sync(mask, pair, 1, G));
+    acc = dadd(acc, __shfl_sync(mask, pair, 2, G));
+    acc = dadd(acc, __shfl_sync(mask, pair, 3, G));
     for (int i = 8 * nch; i < len; ++i)
         acc = dadd(acc, lds_f64(lineb + 8u * (unsigned)(lo + i)));
     return acc;
+}
+
+__device__ __forceinline__ double wsm_nd_sum_line(unsigned lineb, int lo, int len, int lane)
+{
+    return wsm_nd_sum_line<32>(kFull, lineb, lo, len, lane);
 }
 
 // ndarray-order sum of |x[0 .. len)| with element t at W[base(t)], executed by ONE lane.
@@ -281,9 +274,10 @@ __device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, 
 // Branch free: two address selects, two loads, two predicated stores per row.  The per-row
 // scalars (x, y, perm) of positions j and m are exchanged by shuffle (R == 1) or through the
 // scratch line at scrb (R == 2).
-template <int R>
-__device__ __forceinline__ void wsm_swap_positions(unsigned wb, unsigned scrb, const unsigned (&tib)[R],
-                                                   const int (&row)[R], const bool (&rv)[R], int lane,
+template <int G, int R>
+__device__ __forceinline__ void wsm_swap_positions(unsigned mask, unsigned wb, unsigned scrb,
+                                                   const unsigned (&tib)[R], const int (&row)[R],
+                                                   const bool (&rv)[R], int sub,
                                                    int j, int m, unsigned tjb, double (&x)[R],
                                                    double (&y)[R], int (&perm)[R])
 {
@@ -305,10 +299,10 @@ __device__ __forceinline__ void wsm_swap_positions(unsigned wb, unsigned scrb, c
         t2[s] = lds_f64(a2[s]);
     }
     if constexpr (R == 1) {
-        const int partner = (lane == j) ? m : ((lane == m) ? j : lane);
-        x[0] = __shfl_sync(kFull, x[0], partner);
-        y[0] = __shfl_sync(kFull, y[0], partner);
-        perm[0] = __shfl_sync(kFull, perm[0], partner);
+        const int partner = (sub == j) ? m : ((sub == m) ? j : sub);
+        x[0] = __shfl_sync(mask, x[0], partner, G);
+        y[0] = __shfl_sync(mask, y[0], partner, G);
+        perm[0] = __shfl_sync(mask, perm[0], partner, G);
     } else {
 #pragma unroll
         for (int s = 0; s < R; ++s) {
@@ -321,7 +315,7 @@ __device__ __forceinline__ void wsm_swap_positions(unsigned wb, unsigned scrb, c
             }
         }
     }
-    __syncwarp();
+    __syncwarp(mask);
 #pragma unroll
     for (int s = 0; s < R; ++s) {
         sts_f64_if(act[s], a1[s], t2[s]);
@@ -336,52 +330,67 @@ __device__ __forceinline__ void wsm_swap_positions(unsigned wb, unsigned scrb, c
             }
         }
     }
-    __syncwarp();
+    __syncwarp(mask);
 }
 
 // value v[s] of the row at position j, broadcast to the warp
-template <int R>
-__device__ __forceinline__ double wsm_bcast_row(const double (&v)[R], int j)
+template <int G, int R>
+__device__ __forceinline__ double wsm_bcast_row(unsigned mask, const double (&v)[R], int j)
 {
     double x = v[0];
 #pragma unroll
     for (int s = 1; s < R; ++s)
-        if ((j >> 5) == s)
+        if (j / G == s)
             x = v[s];
-    return __shfl_sync(kFull, x, j & 31);
+    return __shfl_sync(mask, x, j % G, G);
 }
 
-template <int kAlgo, int R, bool kStrict, int kWarps, int kMinBlocks>
+// lanes [grp G, grp G + G) of the warp
+template <int G>
+__device__ __forceinline__ unsigned wsm_group_mask(int grp)
+{
+    if constexpr (G == 32)
+        return kFull;
+    else
+        return ((1u << G) - 1u) << (grp * G);
+}
+
+template <int kAlgo, int G, int R, bool kStrict, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
               double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
               int* __restrict__ K)
 {
     extern __shared__ double sm[];
+    // G lanes per matrix, 32 / G matrices per warp; every collective below is confined to the
+    // group (member mask + shuffle width), so the groups of a warp may diverge freely
+    constexpr int kPack = 32 / G;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* W = sm + (size_t)wib * wstride;
+    const int sub = lane & (G - 1), grp = lane / G;
+    const unsigned mask = wsm_group_mask<G>(grp);
+    double* W = sm + (size_t)(wib * kPack + grp) * wstride;
     const unsigned wb = (unsigned)__cvta_generic_to_shared(W);          // byte address of W(0,0)
     const unsigned scrb = wb + 8u * (unsigned)((tri(n) + 1) & ~1);      // 16 doubles of scratch
     const unsigned lineb = scrb + 128u;                                  // 72-entry column line
     const size_t nn = (size_t)n * n;
-    const long long nwarps = (long long)gridDim.x * kWarps;
+    const long long nslots = (long long)gridDim.x * kWarps * kPack;
 
     int row[R];
     unsigned tib[R];   // byte address of W(row, 0)
     bool rv[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        row[s] = lane + 32 * s;
+        row[s] = sub + G * s;
         rv[s] = row[s] < n;
         tib[s] = wb + 8u * (unsigned)tri(rv[s] ? row[s] : 0);
     }
 
-    for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nwarps) {
+    for (long long b = ((long long)blockIdx.x * kWarps + wib) * kPack + grp; b < batch; b += nslots) {
         const double* Ab = A + (size_t)b * nn;
         // ---- load the lower triangle, eight rows per trip (coalesced, loads batched) --------
-        __syncwarp();
-        wsm_load_lower<R, false>(Ab, n, wb, lane);
-        __syncwarp();
+        __syncwarp(mask);
+        wsm_load_lower<G, R, false>(Ab, n, wb, sub);
+        __syncwarp(mask);
 
         double dg[R], g[R], ev[R];
         int perm[R];
@@ -396,16 +405,16 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         }
         bool win[R];
         // gamma = max |a_ii| folded from 0.0 (se90.rs:55-57, se99.rs:54-56)
-        const double gamma = wsm_extreme<true, R>(av, rv, 0.0, win);
+        const double gamma = wsm_extreme<true, R>(mask, av, rv, 0.0, win);
         const double taugamma = dmul(MODCHOL_TAU, gamma);
         double delta_prev = 0.0;
         int kstart = -1;
 
         // exchange of positions j < m: packed triangle + the row scalars dg, g, perm
         auto swap_positions = [&](int j, int m, unsigned tjb, bool /*with_g*/) {
-            wsm_swap_positions<R>(wb, scrb, tib, row, rv, lane, j, m, tjb, dg, g, perm);
+            wsm_swap_positions<G, R>(mask, wb, scrb, tib, row, rv, sub, j, m, tjb, dg, g, perm);
         };
-        auto bcast_row = [&](const double (&v)[R], int j) -> double { return wsm_bcast_row<R>(v, j); };
+        auto bcast_row = [&](const double (&v)[R], int j) -> double { return wsm_bcast_row<G, R>(mask, v, j); };
         // D: s = sqrt(pivot), y such that cs = col*y (FAST) -- see warp_se.cuh
         auto scale = [&](double piv, double& sq, double& y, double& inv_piv) -> bool {
             const bool fast = !kStrict && fast_range_ok(piv);
@@ -510,7 +519,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 if (below)
                     dg[s] = dg_new[s];
             }
-            __syncwarp();
+            __syncwarp(mask);
         };
         int sbase = 0;
 
@@ -523,9 +532,9 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             for (int s = 0; s < R; ++s)
                 active[s] = rv[s] && row[s] >= j;
             double dmax;
-            const int m = wsm_argmax_first<R>(dg, active, row, j, dmax);
+            const int m = wsm_argmax_first<R>(mask, dg, active, row, j, dmax);
             if (kAlgo == kSE99) {  // se99.rs:62-73, before the pivot is applied
-                const double dmin = wsm_extreme<false, R>(dg, active, INFINITY, win);
+                const double dmin = wsm_extreme<false, R>(mask, dg, active, INFINITY, win);
                 if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
                     kstart = j;
                     break;
@@ -549,7 +558,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 // look-ahead value (se90.rs:70-77, se99.rs:82-89); FAST: the updated diagonal
                 nv[s] = fast ? dg_new[s] : dsub(dg[s], ddiv(dmul(col, col), piv));
             }
-            const double la = wsm_extreme<false, R>(nv, below, INFINITY, win);
+            const double la = wsm_extreme<false, R>(mask, nv, below, INFINITY, win);
             const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
             if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
                 kstart = j;
@@ -591,7 +600,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                             lt[s] = lds_f64(tib[s] + 8u * t);   // l_it (rows >= k0 > t)
                             sts_f64_if(rv[s], lineb + 8u * row[s], lt[s]);
                         }
-                        __syncwarp();
+                        __syncwarp(mask);
                         unsigned wr[R];
 #pragma unroll
                         for (int s = 0; s < R; ++s)
@@ -616,7 +625,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                             }
                             lk += 32;
                         }
-                        __syncwarp();
+                        __syncwarp(mask);
                     }
                     sbase = k0;
                 }
@@ -651,7 +660,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                     for (int s = 0; s < R; ++s)
                         active[s] = rv[s] && row[s] >= j;
                     double gmax;  // se90.rs:115, se99.rs:135
-                    const int m = wsm_argmax_first<R>(g, active, row, j, gmax);
+                    const int m = wsm_argmax_first<R>(mask, g, active, row, j, gmax);
                     if (m != j)
                         swap_positions(j, m, tjb, true);
                     double piv = bcast_row(dg, j);
@@ -671,11 +680,11 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
 #pragma unroll
                         for (int s = 0; s < R; ++s)
                             sts_f64_if(rv[s], lineb + 8u * row[s], acol[s]);
-                        __syncwarp();
-                        normj = wsm_nd_sum_line(lineb, j + 1, n - j - 1, lane);
-                        __syncwarp();
+                        __syncwarp(mask);
+                        normj = wsm_nd_sum_line<G>(mask, lineb, j + 1, n - j - 1, sub);
+                        __syncwarp(mask);
                     } else {
-                        normj = warp_sum_tree<32>(kFull, part);
+                        normj = warp_sum_tree<G>(mask, part);
                     }
                     const double ej =
                         max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
@@ -724,7 +733,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 a00 = dsqrt(a00);
                 a10 = ddiv(a10, a00);
                 a11 = dsqrt(dsub(a11, dmul(a10, a10)));
-                __syncwarp();
+                __syncwarp(mask);
 #pragma unroll
                 for (int s = 0; s < R; ++s) {
                     if (row[s] == n - 2) {
@@ -739,17 +748,17 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 }
             }
         }
-        __syncwarp();
+        __syncwarp(mask);
 
         // ---- epilogue: L (strict upper explicitly zero), e un-permuted, p -------------------
-        wsm_store_lower<R>(L + (size_t)b * nn, n, wb, lane);
+        wsm_store_lower<G, R>(L + (size_t)b * nn, n, wb, sub);
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if (rv[s]) {
                 E[(size_t)b * n + perm[s]] = ev[s];                       // se99.rs:194-198
                 P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
             }
-        if (K && lane == 0)
+        if (K && sub == 0)
             K[b] = kstart;
     }
 }

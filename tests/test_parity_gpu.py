@@ -126,12 +126,12 @@ def test_strict_bit_exact_vs_oracle(oracle, torch_cuda, algo, n):
 
 @pytest.mark.parametrize("family", ["reg", "wsm"])
 def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
-    """n <= 32 is served by the register-resident kernels by default; the shared-memory-resident
-    family (default for 32 < n <= 64) must give the same bits there too."""
+    """n <= 32 has two kernel families (shared-memory-resident by default, register-resident on
+    request); both must give the oracle's bits."""
     prev = m.set_small_kernel_family(family)
     try:
         for algo in ALGOS:
-            for n in (1, 2, 5, 8, 16, 17, 31, 32):
+            for n in (1, 2, 3, 4, 5, 8, 9, 16, 17, 31, 32):
                 for mode in ("strict", "fast"):
                     assert m.kernel_class(algo, n, mode) == ("warp32" if family == "reg" else "warp_smem")
                 for fam in ("uniform", "wishart", "ties"):
@@ -140,6 +140,26 @@ def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
                     _assert_bit_exact(f"{family} {algo} n={n} {fam}", _gpu(torch_cuda, algo, a, "strict"), ref)
                     if fam != "ties" and n >= 3:   # exact ties are covered by the tie test
                         _assert_tolerance(f"{family} {algo} n={n} {fam}", a,
+                                          _gpu(torch_cuda, algo, a, "fast"), ref)
+    finally:
+        m.set_small_kernel_family(prev)
+
+
+def test_packed_shared_memory_variant_is_bit_exact(oracle, torch_cuda, monkeypatch):
+    """MODCHOL_WSM_PACK=1: two matrices per warp (16 lanes x 2 rows) for 16 < n <= 32; the two
+    halves of a warp diverge whenever their matrices change phase at different columns, and odd
+    batch sizes leave half a warp without a matrix."""
+    monkeypatch.setenv("MODCHOL_WSM_PACK", "1")
+    prev = m.set_small_kernel_family("wsm")
+    try:
+        for algo in ALGOS:
+            for n, b in ((17, 33), (24, 64), (31, 7), (32, 129)):
+                for fam in ("uniform", "wishart", "pd", "ties"):
+                    a = matgen.make(fam, 5000 + n, b, n)
+                    ref = oracle.factor_batched(algo, a)
+                    _assert_bit_exact(f"packed {algo} n={n} {fam}", _gpu(torch_cuda, algo, a, "strict"), ref)
+                    if fam != "ties":
+                        _assert_tolerance(f"packed {algo} n={n} {fam}", a,
                                           _gpu(torch_cuda, algo, a, "fast"), ref)
     finally:
         m.set_small_kernel_family(prev)
