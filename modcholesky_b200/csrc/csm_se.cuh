@@ -229,33 +229,46 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
         // the same roundings in the same order as the reference's right-looking updates, with
         // read-only shared-memory traffic.  Two __syncthreads (line fill, line release).
         auto left_column = [&](int j, unsigned tjb, int sbase) -> double {
-            const bool mine = rv && row >= sbase && row < j;
-            const double ljs = mine ? lds_f64(tjb + 8u * row) : 0.0;   // row j of L
-            sts_f64_if(mine, lineb + 8u * row, ljs);
-            __syncthreads();
-            double col = lds_f64(tib + 8u * j);
-            int t = sbase;
-            if ((t & 1) && t < j) {
-                col = nmul_add<kStrict>(col, lds_f64(tib + 8u * t), lds_f64(lineb + 8u * t));
-                ++t;
-            }
-            for (; t + 4 <= j; t += 4) {
-                const double2 l01 = lds_v2f64(lineb + 8u * t);
-                const double2 l23 = lds_v2f64(lineb + 8u * t + 16);
-                const double lj[4] = {l01.x, l01.y, l23.x, l23.y};
-                double w[4];
+            // row j of L is read in place (contiguous at tjb, block-wide broadcast loads, LDS.128
+            // once 16-byte aligned); finished rows skip the dot product.  No barrier is needed
+            // here: rows j and the thread's own row were last written before the swap's barrier,
+            // and every consumer of the result goes through a block collective first.
+            double col = 0.0;
+            if (rv && row > j) {
+                col = lds_f64(tib + 8u * j);
+                unsigned rj = tjb + 8u * (unsigned)sbase, ri = tib + 8u * (unsigned)sbase;
+                int left = j - sbase;
+                if ((rj & 8u) && left > 0) {
+                    col = nmul_add<kStrict>(col, lds_f64(ri), lds_f64(rj));
+                    rj += 8;
+                    ri += 8;
+                    --left;
+                }
+                for (; left >= 8; left -= 8) {
+                    const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
+                    const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
+                    const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
+                    double w[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    w[u] = lds_f64(tib + 8u * (t + u));
+                    for (int u = 0; u < 8; ++u)
+                        w[u] = lds_f64(ri + 8u * u);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    col = nmul_add<kStrict>(col, w[u], lj[u]);
+                    for (int u = 0; u < 8; ++u)
+                        col = nmul_add<kStrict>(col, w[u], lj[u]);
+                    rj += 64;
+                    ri += 64;
+                }
+                for (; left >= 2; left -= 2) {
+                    const double2 l01 = lds_v2f64(rj);
+                    const double w0 = lds_f64(ri), w1 = lds_f64(ri + 8);
+                    col = nmul_add<kStrict>(col, w0, l01.x);
+                    col = nmul_add<kStrict>(col, w1, l01.y);
+                    rj += 16;
+                    ri += 16;
+                }
+                if (left)
+                    col = nmul_add<kStrict>(col, lds_f64(ri), lds_f64(rj));
             }
-            for (; t < j; ++t)
-                col = nmul_add<kStrict>(col, lds_f64(tib + 8u * t), lds_f64(lineb + 8u * t));
-            if (!(rv && row > j))
-                col = 0.0;
-            __syncthreads();
             return col;
         };
         // write column j of L (se90.rs:84-87, se99.rs:96-99); the diagonal update is carried in dg

@@ -16,6 +16,8 @@
 // Only the lower triangle of A is read (A symmetric), so DRAM reads drop below the
 // algorithmic 8 n^2 bytes.
 #pragma once
+#include <type_traits>
+
 #include "warp_common.cuh"
 
 namespace modchol {
@@ -439,69 +441,89 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         // start once the block has been materialised for the Gershgorin bounds).
         auto left_column = [&](int j, unsigned tjb, int sbase, double (&col)[R]) {
             // row j of L is contiguous at tjb (W(j, 0..j-1)) and is read by warp-wide broadcast
-            // loads, two columns per LDS.128 once (tjb + 8 t) is 16-byte aligned
+            // loads, two columns per LDS.128 once (tjb + 8 t) is 16-byte aligned.  Finished rows
+            // (<= j) stay out of it: a lane whose rows are all finished skips the dot product
+            // (an idle half warp halves the wavefronts of every LDS.64 of the other half), and a
+            // slice s of rows that is finished in every lane is not evaluated at all.
 #pragma unroll
             for (int s = 0; s < R; ++s)
-                col[s] = lds_f64(tib[s] + 8u * j);
-            unsigned rj = tjb + 8u * (unsigned)sbase;
-            unsigned ri[R];
+                col[s] = 0.0;
+            auto dot = [&](auto s0tag) {
+                constexpr int S0 = decltype(s0tag)::value;
 #pragma unroll
-            for (int s = 0; s < R; ++s)
-                ri[s] = tib[s] + 8u * (unsigned)sbase;
-            int left = j - sbase;
-            auto step1 = [&]() {
-                const double lj = lds_f64(rj);
+                for (int s = S0; s < R; ++s)
+                    col[s] = lds_f64(tib[s] + 8u * j);
+                unsigned rj = tjb + 8u * (unsigned)sbase;
+                unsigned ri[R];
 #pragma unroll
-                for (int s = 0; s < R; ++s)
-                    col[s] = nmul_add<kStrict>(col[s], lds_f64(ri[s]), lj);
-            };
-            auto step2 = [&](unsigned o) {
-                const double2 l01 = lds_v2f64(rj + o);
+                for (int s = S0; s < R; ++s)
+                    ri[s] = tib[s] + 8u * (unsigned)sbase;
+                int left = j - sbase;
+                auto step1 = [&]() {
+                    const double lj = lds_f64(rj);
 #pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    const double w0 = lds_f64(ri[s] + o), w1 = lds_f64(ri[s] + o + 8);
-                    col[s] = nmul_add<kStrict>(col[s], w0, l01.x);
-                    col[s] = nmul_add<kStrict>(col[s], w1, l01.y);
+                    for (int s = S0; s < R; ++s)
+                        col[s] = nmul_add<kStrict>(col[s], lds_f64(ri[s]), lj);
+                };
+                auto step2 = [&](unsigned o) {
+                    const double2 l01 = lds_v2f64(rj + o);
+#pragma unroll
+                    for (int s = S0; s < R; ++s) {
+                        const double w0 = lds_f64(ri[s] + o), w1 = lds_f64(ri[s] + o + 8);
+                        col[s] = nmul_add<kStrict>(col[s], w0, l01.x);
+                        col[s] = nmul_add<kStrict>(col[s], w1, l01.y);
+                    }
+                };
+                auto advance = [&](unsigned bytes) {
+                    rj += bytes;
+#pragma unroll
+                    for (int s = S0; s < R; ++s)
+                        ri[s] += bytes;
+                };
+                if ((rj & 8u) && left > 0) {
+                    step1();
+                    advance(8);
+                    --left;
                 }
-            };
-            auto advance = [&](unsigned bytes) {
-                rj += bytes;
+                for (; left >= 8; left -= 8) {
+                    const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
+                    const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
+                    const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
 #pragma unroll
-                for (int s = 0; s < R; ++s)
-                    ri[s] += bytes;
-            };
-            if ((rj & 8u) && left > 0) {
-                step1();
-                advance(8);
-                --left;
-            }
-            for (; left >= 8; left -= 8) {
-                const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
-                const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
-                const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
+                    for (int s = S0; s < R; ++s) {
+                        double w[8];
 #pragma unroll
-                for (int s = 0; s < R; ++s) {
-                    double w[8];
+                        for (int u = 0; u < 8; ++u)
+                            w[u] = lds_f64(ri[s] + 8u * u);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        w[u] = lds_f64(ri[s] + 8u * u);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        col[s] = nmul_add<kStrict>(col[s], w[u], lj[u]);
+                        for (int u = 0; u < 8; ++u)
+                            col[s] = nmul_add<kStrict>(col[s], w[u], lj[u]);
+                    }
+                    advance(64);
                 }
-                advance(64);
+                if (left & 4) {
+                    step2(0);
+                    step2(16);
+                    advance(32);
+                }
+                if (left & 2) {
+                    step2(0);
+                    advance(16);
+                }
+                if (left & 1)
+                    step1();
+            };
+            if constexpr (R == 1) {
+                if (rv[0] && row[0] > j)
+                    dot(std::integral_constant<int, 0>{});
+            } else {
+                if (j >= G - 1) {   // slice 0 (rows < G) is finished in every lane
+                    if (rv[R - 1] && row[R - 1] > j)
+                        dot(std::integral_constant<int, R - 1>{});
+                } else if (row[R - 1] > j) {
+                    dot(std::integral_constant<int, 0>{});
+                }
             }
-            if (left & 4) {
-                step2(0);
-                step2(16);
-                advance(32);
-            }
-            if (left & 2) {
-                step2(0);
-                advance(16);
-            }
-            if (left & 1)
-                step1();
 #pragma unroll
             for (int s = 0; s < R; ++s)
                 if (!(rv[s] && row[s] > j))
