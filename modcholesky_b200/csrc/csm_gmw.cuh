@@ -9,25 +9,37 @@
 
 namespace modchol {
 
-template <bool kStrict, int kThreads, int kMinBlocks>
+template <bool kStrict, int kThreads, int kMinBlocks, bool kSpill = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
-               double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+               double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
+               double* __restrict__ spill = nullptr, int S = 0)
 {
     extern __shared__ double sm[];
     double* W = sm;
-    const int tpad = (tri(n) + 1) & ~1;
+    using addr_t = typename CsmRows<kSpill>::addr_t;
+    CsmRows<kSpill> rows;   // see csm_se.cuh: rows [0, S) may live in a global spill buffer
+    rows.S = kSpill ? S : 0;
+    rows.triS = tri(rows.S);
+    const int tpad = (tri(n) - rows.triS + 1) & ~1;
     double* linep = W + tpad;
     const int lpad = (n + 8 + 1) & ~1;
     CsmScratch sc = csm_scratch(linep + lpad);
-    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);
-    const unsigned lineb = wb + 8u * (unsigned)tpad;
+    const unsigned wsh = (unsigned)__cvta_generic_to_shared(W);
+    if constexpr (kSpill) {
+        rows.sbase = (unsigned long long)(size_t)W;
+        rows.gb = (unsigned long long)(size_t)(spill + (size_t)blockIdx.x * rows.triS);
+    } else {
+        rows.sbase = wsh;
+        rows.gb = 0;
+    }
+    const unsigned lineb = wsh + 8u * (unsigned)tpad;
     const int tid = threadIdx.x;
     const int nwarps = kThreads >> 5;
     const size_t nn = (size_t)n * n;
     const int row = tid;
     const bool rv = row < n;
-    const unsigned tib = wb + 8u * (unsigned)tri(rv ? row : 0);
+    const addr_t tib = rows.row(rv ? row : 0);
 
     for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
         const double* Ab = A + (size_t)b * nn;
@@ -44,7 +56,7 @@ csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u;
-                sts_f64_if(i < n && tid <= i, wb + 8u * (unsigned)(tri(i) + tid), v[u]);
+                sts_f64_if(i < n && tid <= i, rows.row(i < n ? i : 0) + 8u * (unsigned)tid, v[u]);
                 if (i < n && tid < i)
                     om = fmax(om, fabs(v[u]));
             }
@@ -64,21 +76,21 @@ csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
             dsqrt(fmax(fmax(diag_max, ddiv(off_max, dsqrt(dsub(dmul(nf, nf), 1.0)))), MODCHOL_EPS));
         const double rbeta = kStrict ? 0.0 : ddiv(1.0, beta);
 
-        unsigned tjb = wb;
-        for (int j = 0; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+        addr_t tjb = rows.row(0);
+        for (int j = 0; j < n; tjb = rows.next(tjb, j), ++j) {
             // ---- pivot on max |c_ii| (gmw81.rs:71-78) ---------------------------------------
             const bool active = rv && row >= j;
             double best;
             const int m = csm_argmax_first(sc, nwarps, fabs(cd), active, row, j, best);
             if (m != j) {  // symmetric exchange of positions j < m (see wsm_swap_positions)
-                const unsigned tmb = wb + 8u * (unsigned)tri(m);
+                const addr_t tmb = rows.row(m);
                 const int i = row;
                 const bool act = rv && i != m;
-                unsigned a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
-                unsigned a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
+                addr_t a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
+                addr_t a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
                 if (!act) {
-                    a1 = wb;
-                    a2 = wb;
+                    a1 = tib;
+                    a2 = tib;
                 }
                 const double t1 = lds_f64(a1), t2 = lds_f64(a2);
                 if (i == j || i == m) {
@@ -156,7 +168,7 @@ csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u;
                 if (i < n && tid < n)
-                    Lb[i * n + tid] = (tid <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + tid)) : 0.0;
+                    Lb[i * n + tid] = (tid <= i) ? lds_f64(rows.row(i) + 8u * (unsigned)tid) : 0.0;
             }
         }
         if (rv) {

@@ -33,8 +33,45 @@ static cudaError_t launch_csm(int n, long long batch, const double* a, double* l
     long long blocks = batch;
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every block strides over the batch
-    kern<<<(unsigned)blocks, kThreads, smem, st>>>(n, batch, a, l, e, p, k);
+    kern<<<(unsigned)blocks, kThreads, smem, st>>>(n, batch, a, l, e, p, k, nullptr, 0);
     return cudaGetLastError();
+}
+
+// n above the all-in-shared-memory limit: the first S rows of the packed triangle go to a
+// stream-ordered global buffer (one slice per resident block; it stays in L1/L2)
+template <int kAlgo, bool kStrict, int kThreads>
+static cudaError_t launch_csm_spill(int n, long long batch, const double* a, double* l, double* e,
+                                    unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    auto kern = [] {
+        if constexpr (kAlgo == kGMW81)
+            return csm_gmw_kernel<kStrict, kThreads, 1, true>;
+        else
+            return csm_se_kernel<kAlgo, kStrict, kThreads, 1, true>;
+    }();
+    int dev = 0, optin = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    ce = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (ce != cudaSuccess) return ce;
+    int S = 1;
+    while (S < n && csm_smem_bytes(n, S) > (size_t)optin)
+        ++S;
+    const size_t smem = csm_smem_bytes(n, S);
+    if (smem > (size_t)optin) return cudaErrorInvalidValue;
+    ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              (int)cudaSharedmemCarveoutMaxShared);
+    if (ce != cudaSuccess) return ce;
+    long long blocks = batch < sms ? batch : sms;   // one block per SM, persistent
+    double* spill = nullptr;
+    ce = cudaMallocAsync(&spill, (size_t)blocks * tri(S) * sizeof(double), st);
+    if (ce != cudaSuccess) return ce;
+    kern<<<(unsigned)blocks, kThreads, smem, st>>>(n, batch, a, l, e, p, k, spill, S);
+    ce = cudaGetLastError();
+    const cudaError_t cf = cudaFreeAsync(spill, st);
+    return ce != cudaSuccess ? ce : cf;
 }
 
 #define MODCHOL_CAT2(a, b, c, d) a##b##c##d
@@ -47,7 +84,9 @@ cudaError_t MODCHOL_CAT(launch_csm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
     constexpr bool S = MODCHOL_INST_STRICT != 0;
     if (n <= 128)
         return launch_csm<A, S, 128, 3>(n, batch, a, l, e, p, k, sms, st);
-    return launch_csm<A, S, 256, 1>(n, batch, a, l, e, p, k, sms, st);
+    if (n <= kCsmMaxN)
+        return launch_csm<A, S, 256, 1>(n, batch, a, l, e, p, k, sms, st);
+    return launch_csm_spill<A, S, 256>(n, batch, a, l, e, p, k, sms, st);
 }
 
 }  // namespace modchol

@@ -1,6 +1,9 @@
 // csm_se.cuh -- SE90 / SE99, one thread BLOCK per matrix, matrix resident in shared memory as a
 // packed lower triangle, thread = permuted position (row).  The block-level sibling of
-// wsm_se.cuh for 64 < n <= kThreads (<= 208 with 227 KB of shared memory):
+// wsm_se.cuh for 64 < n <= kThreads (the whole triangle fits 227 KB of shared memory up to
+// n = 236; kSpill keeps the first S rows -- the short ones, dead once their position is
+// eliminated -- in a per-block global-memory buffer that stays in L1/L2, and addresses every
+// row through 64-bit generic addresses):
 //   * same storage (element (i,k) at T(i)+k, conflict-free column access), same branch-free
 //     symmetric swap, same lower-triangle-only update, same STRICT / FAST arithmetic;
 //   * warp collectives become two-level: REDUX inside each warp, one double-buffered exchange
@@ -8,6 +11,8 @@
 //   * n = 128 needs 66 KB instead of the 133 KB of the full-square CTA kernel: three blocks
 //     per SM instead of one.
 #pragma once
+#include <type_traits>
+
 #include "wsm_se.cuh"
 
 namespace modchol {
@@ -132,25 +137,63 @@ __device__ __forceinline__ double csm_sum_tree(CsmScratch& sc, int nwarps, doubl
     return s;
 }
 
-template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks>
+// Row addressing of the block-level kernels.  kSpill = false: 32-bit shared byte addresses, the
+// whole triangle at wb.  kSpill = true: rows [0, S) live in global memory at gb, rows [S, n) in
+// shared memory, all reached through 64-bit generic byte addresses.
+template <bool kSpill>
+struct CsmRows {
+    using addr_t = std::conditional_t<kSpill, unsigned long long, unsigned>;
+    addr_t sbase;            // address of the first shared-memory row (row S)
+    unsigned long long gb;   // address of row 0 in the spill buffer (kSpill only)
+    int S, triS;
+    __device__ __forceinline__ addr_t row(int i) const
+    {
+        if constexpr (kSpill)
+            return i < S ? gb + 8ull * (unsigned)tri(i) : sbase + 8ull * (unsigned)(tri(i) - triS);
+        else
+            return sbase + 8u * (unsigned)tri(i);
+    }
+    // address of row i + 1 given the address of row i
+    __device__ __forceinline__ addr_t next(addr_t a, int i) const
+    {
+        if constexpr (kSpill)
+            return row(i + 1);
+        else
+            return a + 8u * (unsigned)(i + 1);
+    }
+};
+
+template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks, bool kSpill = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
-              double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+              double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
+              double* __restrict__ spill = nullptr, int S = 0)
 {
     extern __shared__ double sm[];
     double* W = sm;
-    const int tpad = (tri(n) + 1) & ~1;
+    using addr_t = typename CsmRows<kSpill>::addr_t;
+    CsmRows<kSpill> rows;
+    rows.S = kSpill ? S : 0;
+    rows.triS = tri(rows.S);
+    const int tpad = (tri(n) - rows.triS + 1) & ~1;
     double* linep = W + tpad;                       // n + 8 entries (scaled pivot column)
     const int lpad = (n + 8 + 1) & ~1;
     CsmScratch sc = csm_scratch(linep + lpad);
-    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);
-    const unsigned lineb = wb + 8u * (unsigned)tpad;
+    const unsigned wsh = (unsigned)__cvta_generic_to_shared(W);
+    if constexpr (kSpill) {
+        rows.sbase = (unsigned long long)(size_t)W;
+        rows.gb = (unsigned long long)(size_t)(spill + (size_t)blockIdx.x * rows.triS);
+    } else {
+        rows.sbase = wsh;
+        rows.gb = 0;
+    }
+    const unsigned lineb = wsh + 8u * (unsigned)tpad;
     const int tid = threadIdx.x, lane = tid & 31;
     const int nwarps = kThreads >> 5;
     const size_t nn = (size_t)n * n;
     const int row = tid;
     const bool rv = row < n;
-    const unsigned tib = wb + 8u * (unsigned)tri(rv ? row : 0);
+    const addr_t tib = rows.row(rv ? row : 0);
 
     for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
         const double* Ab = A + (size_t)b * nn;
@@ -166,7 +209,7 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u;
-                sts_f64_if(i < n && tid <= i, wb + 8u * (unsigned)(tri(i) + tid), v[u]);
+                sts_f64_if(i < n && tid <= i, rows.row(i < n ? i : 0) + 8u * (unsigned)tid, v[u]);
             }
         }
         __syncthreads();
@@ -182,15 +225,15 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
         int kstart = -1;
 
         // symmetric exchange of positions j < m (see wsm_swap_positions) + row scalars
-        auto swap_positions = [&](int j, int m, unsigned tjb) {
-            const unsigned tmb = wb + 8u * (unsigned)tri(m);
+        auto swap_positions = [&](int j, int m, addr_t tjb) {
+            const addr_t tmb = rows.row(m);
             const int i = row;
             const bool act = rv && i != m;
-            unsigned a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
-            unsigned a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
+            addr_t a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
+            addr_t a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
             if (!act) {
-                a1 = wb;
-                a2 = wb;
+                a1 = tib;
+                a2 = tib;
             }
             const double t1 = lds_f64(a1), t2 = lds_f64(a2);
             if (i == j || i == m) {
@@ -228,7 +271,7 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
         //     col_i = a_ij - l_i,sbase l_j,sbase - ... - l_i,j-1 l_j,j-1      (in this order),
         // the same roundings in the same order as the reference's right-looking updates, with
         // read-only shared-memory traffic.  Two __syncthreads (line fill, line release).
-        auto left_column = [&](int j, unsigned tjb, int sbase) -> double {
+        auto left_column = [&](int j, addr_t tjb, int sbase) -> double {
             // row j of L is read in place (contiguous at tjb, block-wide broadcast loads, LDS.128
             // once 16-byte aligned); finished rows skip the dot product.  No barrier is needed
             // here: rows j and the thread's own row were last written before the swap's barrier,
@@ -236,7 +279,7 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             double col = 0.0;
             if (rv && row > j) {
                 col = lds_f64(tib + 8u * j);
-                unsigned rj = tjb + 8u * (unsigned)sbase, ri = tib + 8u * (unsigned)sbase;
+                addr_t rj = tjb + 8u * (unsigned)sbase, ri = tib + 8u * (unsigned)sbase;
                 int left = j - sbase;
                 if ((rj & 8u) && left > 0) {
                     col = nmul_add<kStrict>(col, lds_f64(ri), lds_f64(rj));
@@ -272,7 +315,7 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             return col;
         };
         // write column j of L (se90.rs:84-87, se99.rs:96-99); the diagonal update is carried in dg
-        auto eliminate = [&](int j, unsigned tjb, double sq, double cs, double dg_new) {
+        auto eliminate = [&](int j, addr_t tjb, double sq, double cs, double dg_new) {
             const bool below = rv && row > j;
             sts_f64_if(below || row == j, below ? tib + 8u * j : tjb + 8u * j, below ? cs : sq);
             if (below)
@@ -292,8 +335,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
 
         // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
         int j = 0;
-        unsigned tjb = wb;
-        for (; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+        addr_t tjb = rows.row(0);
+        for (; j < n; tjb = rows.next(tjb, j), ++j) {
             const bool active = rv && row >= j;
             double dmax;
             const int m = csm_argmax_first(sc, nwarps, dg, active, row, j, dmax);
@@ -345,7 +388,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                         const double lt = lds_f64(tib + 8u * t);
                         sts_f64_if(rv, lineb + 8u * row, lt);
                         __syncthreads();
-                        unsigned wr = tib + 8u * kk0, lk = lineb + 8u * kk0;
+                        addr_t wr = tib + 8u * kk0;
+                        unsigned lk = lineb + 8u * kk0;
                         for (int k = kk0; k < kend; k += 4) {
                             const double2 c01 = lds_v2f64(lk);
                             const double2 c23 = lds_v2f64(lk + 16);
@@ -368,24 +412,26 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                 }
                 // se90.rs:105-110, se99.rs:125-130
                 if (rv && row >= k0) {
-                    const int i = row, tis = tri(row);
+                    const int i = row;
                     if constexpr (kStrict) {
-                        const double s1 = wsm_nd_sum_abs_lane(W, i - k0, [&](int t) { return tis + k0 + t; });
-                        const double s2 = wsm_nd_sum_abs_lane(W, n - 1 - i, [&](int t) { return tri(i + 1 + t) + i; });
+                        const double s1 =
+                            wsm_nd_sum_abs_fn(i - k0, [&](int t) { return lds_f64(tib + 8u * (unsigned)(k0 + t)); });
+                        const double s2 = wsm_nd_sum_abs_fn(
+                            n - 1 - i, [&](int t) { return lds_f64(rows.row(i + 1 + t) + 8u * (unsigned)i); });
                         g = dsub(dsub(dg, s1), s2);
                     } else {
                         double s1 = 0.0, s2 = 0.0;
                         for (int c = k0; c < i; ++c)
                             s1 = dadd(s1, fabs(lds_f64(tib + 8u * c)));
-                        unsigned tr = wb + 8u * (unsigned)(tri(i + 1) + i);
+                        addr_t tr = (i + 1 < n) ? rows.row(i + 1) : tib;
                         for (int r = i + 1; r < n; ++r) {
-                            s2 = dadd(s2, fabs(lds_f64(tr)));
-                            tr += 8u * (unsigned)(r + 1);
+                            s2 = dadd(s2, fabs(lds_f64(tr + 8u * (unsigned)i)));
+                            tr = rows.next(tr, r);
                         }
                         g = dsub(dg, dadd(s1, s2));
                     }
                 }
-                for (j = k0; j + 2 < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+                for (j = k0; j + 2 < n; tjb = rows.next(tjb, j), ++j) {
                     const bool active = rv && row >= j;
                     double gmax;  // se90.rs:115, se99.rs:135
                     const int m = csm_argmax_first(sc, nwarps, g, active, row, j, gmax);
@@ -439,8 +485,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                 // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186)
                 double a00 = bcast_row(dg, n - 2);
                 double a11 = bcast_row(dg, n - 1);
-                const unsigned a10b = wb + 8u * (unsigned)(tri(n - 1) + n - 2);
-                const double c2 = left_column(n - 2, wb + 8u * (unsigned)tri(n - 2), sbase);
+                const addr_t a10b = rows.row(n - 1) + 8u * (unsigned)(n - 2);
+                const double c2 = left_column(n - 2, rows.row(n - 2), sbase);
                 double a10 = bcast_row(c2, n - 1);
                 double lhi, llo;
                 eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);
@@ -473,7 +519,7 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u;
                 if (i < n && tid < n)
-                    Lb[i * n + tid] = (tid <= i) ? lds_f64(wb + 8u * (unsigned)(tri(i) + tid)) : 0.0;
+                    Lb[i * n + tid] = (tid <= i) ? lds_f64(rows.row(i) + 8u * (unsigned)tid) : 0.0;
             }
         }
         if (rv) {
@@ -485,9 +531,11 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
     }
 }
 
-__host__ inline size_t csm_smem_bytes(int n)
+// shared memory of one block when rows [0, S) are spilled (S = 0: nothing spilled)
+__host__ inline size_t csm_smem_bytes(int n, int S = 0)
 {
-    return (size_t)(((tri(n) + 1) & ~1) + ((n + 8 + 1) & ~1) + csm_scratch_doubles()) * sizeof(double);
+    return (size_t)(((tri(n) - tri(S) + 1) & ~1) + ((n + 8 + 1) & ~1) + csm_scratch_doubles()) *
+           sizeof(double);
 }
 
 }  // namespace modchol

@@ -77,12 +77,13 @@ MODCHOL_DECL_CSM(1, 0)
 MODCHOL_DECL_CSM(2, 1)
 MODCHOL_DECL_CSM(2, 0)
 
-constexpr int kCsmMaxN = 236;   // packed triangle + line + scratch <= 227 KB
+constexpr int kCsmMaxN = 236;        // packed triangle + line + scratch <= 227 KB
+constexpr int kCsmSpillMaxN = 256;   // one thread per row, 256 threads; first rows spilled to L2
 
 inline bool csm_kernel_available(int algo, int mode, int n)
 {
     (void)mode;
-    return n > 64 && n <= kCsmMaxN && algo >= 0 && algo <= 2;
+    return n > 64 && n <= kCsmSpillMaxN && algo >= 0 && algo <= 2;
 }
 
 inline cudaError_t launch_csm_kernel(int algo, int mode, int n, long long batch, const double* a,

@@ -14,8 +14,8 @@
 namespace modchol {
 
 // sum_{s<j} line[s] * W(i,s) for one row (byte address rowb), ndarray order or FMA chains
-template <bool kStrict>
-__device__ __forceinline__ double wsm_gmw_dot(unsigned lineb, unsigned rowb, int j)
+template <bool kStrict, typename AddrT>
+__device__ __forceinline__ double wsm_gmw_dot(unsigned lineb, AddrT rowb, int j)
 {
     if constexpr (kStrict) {
         double p[8];

@@ -131,6 +131,30 @@ __device__ __forceinline__ void sts_f64_if(bool pred, unsigned a, double v)
                  :: "r"(a), "d"(v), "r"((int)pred) : "memory");
 }
 
+// The same accessors on 64-bit GENERIC byte addresses (shared or global window), for the
+// block-level kernels whose first rows are spilled to global memory (csm_se.cuh, n > 236).
+__device__ __forceinline__ double lds_f64(unsigned long long a)
+{
+    double v;
+    asm volatile("ld.f64 %0, [%1];" : "=d"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned long long a)
+{
+    double2 v;
+    asm volatile("ld.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned long long a, double v)
+{
+    asm volatile("st.f64 [%0], %1;" :: "l"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f64_if(bool pred, unsigned long long a, double v)
+{
+    asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.f64 [%0], %1;\n}"
+                 :: "l"(a), "d"(v), "r"((int)pred) : "memory");
+}
+
 // ld.shared.f64 where pred, else 0.0 -- one predicated load into a zeroed register
 __device__ __forceinline__ double lds_f64_or_zero(bool pred, unsigned a)
 {
@@ -245,9 +269,9 @@ __device__ __forceinline__ double wsm_nd_sum_line(unsigned lineb, int lo, int le
     return wsm_nd_sum_line<32>(kFull, lineb, lo, len, lane);
 }
 
-// ndarray-order sum of |x[0 .. len)| with element t at W[base(t)], executed by ONE lane.
-template <typename AddrFn>
-__device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, AddrFn addr)
+// ndarray-order sum of |val(0)|, ..., |val(len-1)|, executed by ONE lane.
+template <typename ValFn>
+__device__ __forceinline__ double wsm_nd_sum_abs_fn(int len, ValFn val)
 {
     double p[8];
 #pragma unroll
@@ -257,7 +281,7 @@ __device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, 
     for (; t + 8 <= len; t += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            p[u] = dadd(p[u], fabs(W[addr(t + u)]));
+            p[u] = dadd(p[u], fabs(val(t + u)));
     }
     double acc = 0.0;
     acc = dadd(acc, dadd(p[0], p[4]));
@@ -265,8 +289,15 @@ __device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, 
     acc = dadd(acc, dadd(p[2], p[6]));
     acc = dadd(acc, dadd(p[3], p[7]));
     for (; t < len; ++t)
-        acc = dadd(acc, fabs(W[addr(t)]));
+        acc = dadd(acc, fabs(val(t)));
     return acc;
+}
+
+// same with element t at W[addr(t)]
+template <typename AddrFn>
+__device__ __forceinline__ double wsm_nd_sum_abs_lane(const double* W, int len, AddrFn addr)
+{
+    return wsm_nd_sum_abs_fn(len, [&](int t) { return W[addr(t)]; });
 }
 
 // Symmetric exchange of positions j < m in the packed lower triangle (utils.rs:30-49):

@@ -36,9 +36,9 @@ def test_header_and_library_agree():
 
 def test_version_and_kernel_classes():
     assert m.lib().modchol_version() == 100
-    assert m.kernel_class("gmw81", 256) in ("cta_gmem", "cluster")
+    assert m.kernel_class("gmw81", 256) == "cta_packed" and m.kernel_class("gmw81", 257) == "cta_gmem"
     assert m.kernel_class("se99", 128) == "cta_packed" and m.kernel_class("se90", 236) == "cta_packed"
-    assert m.kernel_class("se90", 237) == "cta_gmem" and m.kernel_class("gmw81", 128) == "cta_packed"
+    assert m.kernel_class("se90", 237) == "cta_packed" and m.kernel_class("gmw81", 128) == "cta_packed"
     assert m.kernel_class("se90", 64) == "warp_smem"
     assert m.kernel_class("se99", 32, "fast") == "warp_smem" and m.kernel_class("gmw81", 64) == "warp_smem"
     assert m.kernel_class("gmw81", 65) == "cta_packed"

@@ -69,7 +69,19 @@ def _assert_tolerance(tag, a, got, ref):
     ep = np.take_along_axis(e, idx, 1)
     rhs = ap + np.einsum("bi,ij->bij", ep, np.eye(n))
     res = np.abs(llt - rhs).max(axis=(1, 2)) / anorm
-    assert (res[ok] <= TOL_RECON).all(), f"{tag}: reconstruction {res[ok].max():.3e} > 1e-12"
+    # Where ||A + E|| >> ||A|| (GMW81 at n = 256 adds E ~ 1e3 ||A||) evaluating L L^T in f64 is
+    # itself off by more than 1e-12 ||A||: the bar is then the reference's own residual, computed
+    # the same way from the oracle's factors.
+    lr = ref.l
+    idr = ref.p.astype(np.int64)
+    apr = np.take_along_axis(np.take_along_axis(a, idr[:, :, None], 1), idr[:, None, :], 2)
+    rhr = apr + np.einsum("bi,ij->bij", np.take_along_axis(ref.e, idr, 1), np.eye(n))
+    with np.errstate(invalid="ignore"):
+        res_ref = np.abs(lr @ np.transpose(lr, (0, 2, 1)) - rhr).max(axis=(1, 2)) / anorm
+    # ... and never below a few ulps of the largest entry of A + E (the diagonal L L^T must hit)
+    ulps = 8.0 * np.finfo(np.float64).eps * np.nan_to_num(np.abs(rhr).max(axis=(1, 2))) / anorm
+    bar = np.maximum(np.maximum(TOL_RECON, 2.0 * np.nan_to_num(res_ref)), ulps)
+    assert (res[ok] <= bar[ok]).all(), f"{tag}: reconstruction {res[ok].max():.3e} > max(1e-12, 2x reference's, 8 ulp of |A+E|)"
     assert (np.triu(l, 1) == 0).all() and (e[ok] >= 0).all()
 
 
@@ -166,7 +178,7 @@ def test_packed_shared_memory_variant_is_bit_exact(oracle, torch_cuda, monkeypat
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("n", [160, 200, 236, 237, 256])
+@pytest.mark.parametrize("n", [160, 200, 236, 237, 250, 256, 257, 300])
 def test_strict_bit_exact_large(oracle, torch_cuda, algo, n):
     for fam in ("uniform", "wishart"):
         a = matgen.make(fam, 2000 + n, 6, n)
@@ -175,7 +187,7 @@ def test_strict_bit_exact_large(oracle, torch_cuda, algo, n):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("n", [2, 3, 6, 8, 13, 16, 24, 32, 48, 64, 100, 150])
+@pytest.mark.parametrize("n", [2, 3, 6, 8, 13, 16, 24, 32, 48, 64, 100, 150, 256])
 def test_fast_mode_within_north_star_tolerances(oracle, torch_cuda, algo, n):
     b = 512 if n <= 32 else (64 if n <= 64 else 16)
     for fam in ("uniform", "wishart", "pd", "bench"):
@@ -349,7 +361,11 @@ def test_full_size_properties(oracle, torch_cuda, algo, n, batch, fam, mode):
     resid, flags = m.verify_batched(a, d)
     torch.cuda.synchronize()
     assert int(flags.max()) == 0, "p not a permutation / e < 0 / dirty upper triangle / NaN"
-    assert float(resid.max()) <= TOL_RECON, float(resid.max())
+    # 1e-12 ||A||, or a few ulps of the largest entry of A + E where E dwarfs A (GMW81, n = 256)
+    amax = a.abs().amax(dim=(1, 2))
+    bar = torch.clamp(8.0 * np.finfo(np.float64).eps * (amax + d.e.amax(dim=1)) / torch.clamp(amax, min=1.0),
+                      min=TOL_RECON)
+    assert bool((resid <= bar).all()), float((resid / bar).max())
     # cross-check the on-device verifier itself and the kernel on a sampled subset
     sel = torch.randint(0, batch, (64,), generator=torch.Generator().manual_seed(5)).tolist()
     asub = a[sel].cpu().numpy()
