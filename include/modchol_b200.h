@@ -116,6 +116,18 @@ int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const doub
                               const uint64_t *p, const double *b, double *x, int mem_kind,
                               void *stream);
 
+/* The same consumer step FUSED with the factorisation: factorise a_b with `algo` and solve
+ * (A_b + E_b) x = b for nrhs right-hand sides per matrix in one call.  For n <= 64 this is ONE
+ * kernel and the factor never leaves shared memory, so L does not round-trip through HBM
+ * (n = 32: 6.4 KB read + 0.25 KB written per matrix instead of 16.9 KB + the solve's 8.5 KB);
+ * larger n run the factor kernel into scratch followed by the solve kernel.
+ *   b, x : batch x nrhs x n f64; x may alias b.
+ *   l, e, p, phase2_start : optional outputs as in modchol_factor_batched_f64 (NULL = not wanted). */
+int modchol_factor_solve_batched_f64(int algo, int mode, int64_t batch, int32_t n, int32_t nrhs,
+                                     const double *a, const double *b, double *x, double *l,
+                                     double *e, uint64_t *p, int32_t *phase2_start, int mem_kind,
+                                     void *stream);
+
 /* Name of the kernel class the dispatcher uses for (algo, mode, n) -- e.g. "warp32",
  * "cta_smem", "cta_gmem" -- for logging and tests.  Never NULL. */
 const char *modchol_kernel_class(int algo, int mode, int32_t n);

@@ -10,7 +10,8 @@ from ._lib import (  # noqa: F401
     GMW81, SE90, SE99, MEM_DEVICE, MEM_HOST, MODE_FAST, MODE_STRICT, ModCholError, lib)
 from .api import (  # noqa: F401
     Array2, Array3, Decomposition, GershgorinCircles, ModCholeskyGMW81, ModCholeskySE90,
-    ModCholeskySE99, NotSquareError, factor, factor_batched, gershgorin_circles_batched,
+    ModCholeskySE99, NotSquareError, factor, factor_batched, factor_solve_batched,
+    gershgorin_circles_batched,
     mod_cholesky_gmw81, mod_cholesky_se90, mod_cholesky_se99, solve_batched, verify_batched)
 
 __version__ = "0.1.0"

@@ -25,6 +25,7 @@ EXPORTS = (
     "modchol_gershgorin_circles_batched_f64",
     "modchol_verify_batched_f64",
     "modchol_solve_batched_f64",
+    "modchol_factor_solve_batched_f64",
     "modchol_kernel_class",
     "modchol_set_small_kernel_family",
     "modchol_launch_count",
@@ -69,6 +70,9 @@ def lib() -> ctypes.CDLL:
     L.modchol_verify_batched_f64.restype = ctypes.c_int
     L.modchol_solve_batched_f64.argtypes = [i64, i32, i32, vp, vp, vp, vp, ctypes.c_int, vp]
     L.modchol_solve_batched_f64.restype = ctypes.c_int
+    L.modchol_factor_solve_batched_f64.argtypes = [ctypes.c_int, ctypes.c_int, i64, i32, i32, vp, vp, vp,
+                                                   vp, vp, vp, vp, ctypes.c_int, vp]
+    L.modchol_factor_solve_batched_f64.restype = ctypes.c_int
     L.modchol_kernel_class.argtypes = [ctypes.c_int, ctypes.c_int, i32]
     L.modchol_kernel_class.restype = ctypes.c_char_p
     L.modchol_set_small_kernel_family.argtypes = [ctypes.c_int]

@@ -209,6 +209,57 @@ def solve_batched(d: Decomposition, b):
     return x[:, 0, :] if squeeze else x
 
 
+def factor_solve_batched(algo, a, b, mode="strict", return_factors: bool = False):
+    """Factorise every a[i] with `algo` and solve (A + E) x = b in the same call (for n <= 64 in
+    the same kernel: the factor stays in shared memory).  `a`: (batch, n, n); `b`: (batch, n) or
+    (batch, nrhs, n); returns x shaped like b, plus the Decomposition when `return_factors`."""
+    if a.ndim != 3 or a.shape[1] != a.shape[2]:
+        raise NotSquareError(f"expected (batch, n, n), got {tuple(a.shape)}")
+    L = _lib.lib()
+    ai, mi = _lib.algo_id(algo), _lib.mode_id(mode)
+    squeeze = b.ndim == 2
+    if squeeze:
+        b = b[:, None, :]
+    bt, nrhs, n = b.shape
+    if bt != a.shape[0] or n != a.shape[1]:
+        raise ValueError(f"b of shape {tuple(b.shape)} does not match a of shape {tuple(a.shape)}")
+    d = None
+    if _is_torch(a):
+        import torch
+        a, b = a.contiguous(), b.contiguous()
+        with torch.cuda.device(a.device):
+            x = torch.empty_like(b)
+            ptrs = [None, None, None, None]
+            if return_factors:
+                l = torch.empty_like(a)
+                e = torch.empty((bt, n), dtype=torch.float64, device=a.device)
+                p = torch.empty((bt, n), dtype=torch.int64, device=a.device)
+                k = torch.empty((bt,), dtype=torch.int32, device=a.device)
+                ptrs = [t.data_ptr() for t in (l, e, p, k)]
+                d = Decomposition(l, e, p, k)
+            st = torch.cuda.current_stream(a.device).cuda_stream
+            rc = L.modchol_factor_solve_batched_f64(ai, mi, bt, n, nrhs, a.data_ptr(), b.data_ptr(),
+                                                    x.data_ptr(), *ptrs, _lib.MEM_DEVICE,
+                                                    ctypes.c_void_p(st))
+        _lib.check(rc)
+    else:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty_like(b)
+        ptrs = [None, None, None, None]
+        if return_factors:
+            l = np.empty_like(a)
+            e = np.empty((bt, n), dtype=np.float64)
+            p = np.empty((bt, n), dtype=np.uint64)
+            k = np.empty((bt,), dtype=np.int32)
+            ptrs = [t.ctypes.data for t in (l, e, p, k)]
+            d = Decomposition(l, e, p, k)
+        _lib.check(L.modchol_factor_solve_batched_f64(ai, mi, bt, n, nrhs, a.ctypes.data, b.ctypes.data,
+                                                      x.ctypes.data, *ptrs, _lib.MEM_HOST, None))
+    x = x[:, 0, :] if squeeze else x
+    return (x, d) if return_factors else x
+
+
 # ---- the reference's trait spelling -----------------------------------------------------
 class ModCholeskyGMW81:
     """gmw81.rs:24-32: the default body panics with "Not implemented!"."""

@@ -297,6 +297,56 @@ int check_common(int algo, int mode, long long batch, int n, const void* a, cons
     return MODCHOL_OK;
 }
 
+// Factorise and solve with device pointers.  n <= 64 (shared-memory warp kernels): ONE kernel, the
+// factor never leaves shared memory unless l is asked for.  Otherwise: factor kernel into l / p
+// (stream-ordered scratch when the caller passes NULL), then the batched solve kernel.
+int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int nrhs,
+                        const double* a, const double* b, double* x, double* l, double* e,
+                        unsigned long long* p, int* k, cudaStream_t st)
+{
+    if (batch == 0)
+        return MODCHOL_OK;
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    const DeviceCtx& c = g_ctx[dev];
+    if (classify(algo, mode, n, c.smem_optin) == kClsWarpSmem) {
+        cudaError_t ce = launch_wsm_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st, b, x, nrhs);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "fused factor+solve launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    const size_t nn = (size_t)n * n;
+    double *lt = nullptr, *et = nullptr;
+    unsigned long long* pt = nullptr;
+    cudaError_t ce = cudaSuccess;
+    if (!l) ce = cudaMallocAsync(&lt, (size_t)batch * nn * sizeof(double), st);
+    if (ce == cudaSuccess && !e) ce = cudaMallocAsync(&et, (size_t)batch * n * sizeof(double), st);
+    if (ce == cudaSuccess && !p) ce = cudaMallocAsync(&pt, (size_t)batch * n * sizeof(unsigned long long), st);
+    if (ce == cudaSuccess) {
+        double* lw = l ? l : lt;
+        unsigned long long* pw = p ? p : pt;
+        rc = factor_device(dev, algo, mode, batch, n, a, lw, e ? e : et, pw, k, st);
+        if (rc == MODCHOL_OK) {
+            const size_t smem = (size_t)4 * n * sizeof(double);
+            const long long total = batch * (long long)nrhs;
+            const unsigned grid = (unsigned)std::min<long long>((total + 3) / 4, (long long)c.sms * 16);
+            solve_kernel<<<grid, 128, smem, st>>>(batch, n, nrhs, lw, pw, b, x);
+            g_launches.fetch_add(1);
+            ce = cudaGetLastError();
+        }
+    }
+    if (lt) cudaFreeAsync(lt, st);
+    if (et) cudaFreeAsync(et, st);
+    if (pt) cudaFreeAsync(pt, st);
+    if (rc)
+        return rc;
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "factor+solve: %s", cudaGetErrorString(ce));
+    return MODCHOL_OK;
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -579,6 +629,69 @@ int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const doub
     cudaFree(dl); cudaFree(dp); cudaFree(db);
     if (ce != cudaSuccess)
         return fail(MODCHOL_ERR_CUDA, "solve: %s", cudaGetErrorString(ce));
+    return MODCHOL_OK;
+}
+
+int modchol_factor_solve_batched_f64(int algo, int mode, int64_t batch, int32_t n, int32_t nrhs,
+                                     const double* a, const double* b, double* x, double* l,
+                                     double* e, uint64_t* p, int32_t* phase2_start, int mem_kind,
+                                     void* stream)
+{
+    g_err.clear();
+    int rc = check_common(algo, mode, batch, n, a, a, a, a);   // l, e, p are optional here
+    if (rc)
+        return rc;
+    if (nrhs < 1 || (batch > 0 && (!b || !x)))
+        return fail(MODCHOL_ERR_BAD_ARG, "factor_solve: nrhs >= 1 and non-null b, x required");
+    if (mem_kind != MODCHOL_MEM_HOST && mem_kind != MODCHOL_MEM_DEVICE)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown mem_kind %d", mem_kind);
+    if (device_count() < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (batch == 0)
+        return MODCHOL_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= kMaxDevices)
+        return fail(MODCHOL_ERR_UNSUPPORTED, "device index %d too large", dev);
+    auto pu = reinterpret_cast<unsigned long long*>(p);
+    if (mem_kind == MODCHOL_MEM_DEVICE)
+        return factor_solve_device(dev, algo, mode, batch, n, nrhs, a, b, x, l, e, pu, phase2_start,
+                                   static_cast<cudaStream_t>(stream));
+    // host pointers: chunks of at most ~256 MB of input through plain device buffers
+    const size_t nn = (size_t)n * n;
+    const long long per = std::max<long long>(1, (long long)((256ull << 20) / (nn * sizeof(double))));
+    const long long cmax = std::min<long long>(per, batch);
+    const size_t rb = (size_t)nrhs * n * sizeof(double);
+    double *da = nullptr, *db = nullptr, *dl = nullptr, *de = nullptr;
+    unsigned long long* dp = nullptr;
+    int* dk = nullptr;
+    cudaError_t ce = cudaMalloc(&da, cmax * nn * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc(&db, cmax * rb);
+    if (ce == cudaSuccess && l) ce = cudaMalloc(&dl, cmax * nn * sizeof(double));
+    if (ce == cudaSuccess && e) ce = cudaMalloc(&de, cmax * n * sizeof(double));
+    if (ce == cudaSuccess && p) ce = cudaMalloc(&dp, cmax * n * sizeof(unsigned long long));
+    if (ce == cudaSuccess && phase2_start) ce = cudaMalloc(&dk, cmax * sizeof(int));
+    rc = MODCHOL_OK;
+    for (long long o = 0; ce == cudaSuccess && rc == MODCHOL_OK && o < batch; o += cmax) {
+        const long long cnt = std::min<long long>(cmax, batch - o);
+        ce = cudaMemcpy(da, a + o * nn, cnt * nn * sizeof(double), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpy(db, b + (size_t)o * nrhs * n, cnt * rb, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) break;
+        rc = factor_solve_device(dev, algo, mode, cnt, n, nrhs, da, db, db, dl, de, dp, dk, nullptr);
+        if (rc) break;
+        ce = cudaMemcpy(x + (size_t)o * nrhs * n, db, cnt * rb, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess && l) ce = cudaMemcpy(l + o * nn, dl, cnt * nn * sizeof(double), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess && e) ce = cudaMemcpy(e + o * n, de, cnt * n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess && p) ce = cudaMemcpy(p + o * n, dp, cnt * n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess && phase2_start)
+            ce = cudaMemcpy(phase2_start + o, dk, cnt * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(da); cudaFree(db); cudaFree(dl); cudaFree(de); cudaFree(dp); cudaFree(dk);
+    if (rc)
+        return rc;
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "factor_solve: %s", cudaGetErrorString(ce));
     return MODCHOL_OK;
 }
 

@@ -32,7 +32,8 @@ MODCHOL_DECL_WARP(2, 0)
 // shared-memory-resident warp kernels (wsm_se.cuh, wsm_gmw.cuh), n <= 64; defined in wsm_inst.cu
 #define MODCHOL_DECL_WSM(A, S)                                                                   \
     cudaError_t launch_wsm_a##A##_s##S(int n, long long batch, const double* a, double* l,       \
-                                       double* e, unsigned long long* p, int* k, int sms,        \
+                                       double* e, unsigned long long* p, int* k,                 \
+                                       const double* rhs, double* x, int nrhs, int sms,          \
                                        cudaStream_t st);
 MODCHOL_DECL_WSM(0, 1)
 MODCHOL_DECL_WSM(0, 0)
@@ -47,20 +48,22 @@ inline bool wsm_kernel_available(int algo, int mode, int n)
     return n >= 1 && n <= 64 && algo >= 0 && algo <= 2;
 }
 
+// l, e, p, k may each be NULL; x != NULL adds the fused solve of (A + E) x = rhs (nrhs per matrix)
 inline cudaError_t launch_wsm_kernel(int algo, int mode, int n, long long batch, const double* a,
                                      double* l, double* e, unsigned long long* p, int* k, int sms,
-                                     cudaStream_t st)
+                                     cudaStream_t st, const double* rhs = nullptr,
+                                     double* x = nullptr, int nrhs = 0)
 {
     const bool strict = mode == 0;
     if (algo == 0)
-        return strict ? launch_wsm_a0_s1(n, batch, a, l, e, p, k, sms, st)
-                      : launch_wsm_a0_s0(n, batch, a, l, e, p, k, sms, st);
+        return strict ? launch_wsm_a0_s1(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
+                      : launch_wsm_a0_s0(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (algo == 1)
-        return strict ? launch_wsm_a1_s1(n, batch, a, l, e, p, k, sms, st)
-                      : launch_wsm_a1_s0(n, batch, a, l, e, p, k, sms, st);
+        return strict ? launch_wsm_a1_s1(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
+                      : launch_wsm_a1_s0(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (algo == 2)
-        return strict ? launch_wsm_a2_s1(n, batch, a, l, e, p, k, sms, st)
-                      : launch_wsm_a2_s0(n, batch, a, l, e, p, k, sms, st);
+        return strict ? launch_wsm_a2_s1(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
+                      : launch_wsm_a2_s0(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     return cudaErrorNotSupported;
 }
 

@@ -70,7 +70,7 @@ template <int G, int R, bool kStrict, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
-               int* __restrict__ K)
+               int* __restrict__ K, const double* __restrict__ Bm, double* __restrict__ X, int nrhs)
 {
     extern __shared__ double sm[];
     constexpr int kPack = 32 / G;   // matrices per warp, G lanes each (see wsm_se.cuh)
@@ -206,15 +206,21 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
 
         // ---- epilogue ---------------------------------------------------------------------
         __syncwarp(mask);
-        wsm_store_lower<G, R>(L + (size_t)b * nn, n, wb, sub);
+        if (L)
+            wsm_store_lower<G, R>(L + (size_t)b * nn, n, wb, sub);
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if (rv[s]) {
-                E[(size_t)b * n + perm[s]] = ev[s];                          // gmw81.rs:127-131
-                P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
+                if (E)
+                    E[(size_t)b * n + perm[s]] = ev[s];                      // gmw81.rs:127-131
+                if (P)
+                    P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
             }
         if (K && sub == 0)
             K[b] = -1;
+        if (X)   // fused solve, see wsm_solve_in_place
+            wsm_solve_in_place<G, R>(mask, n, wb, tib, row, rv, perm, Bm + (size_t)b * nrhs * n,
+                                     X + (size_t)b * nrhs * n, nrhs);
     }
 }
 

@@ -20,7 +20,8 @@ namespace modchol {
 
 template <int kAlgo, int G, int R, bool kStrict>
 static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l, double* e,
-                              unsigned long long* p, int* k, int sms, cudaStream_t st)
+                              unsigned long long* p, int* k, const double* rhs, double* x, int nrhs,
+                              int sms, cudaStream_t st)
 {
     constexpr int kWarps = 4;
     constexpr int kPack = 32 / G;   // matrices per warp
@@ -48,7 +49,7 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
     long long blocks = (batch + kWarps * kPack - 1) / (kWarps * kPack);
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every lane group strides over the batch
-    kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(n, wstride, batch, a, l, e, p, k);
+    kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(n, wstride, batch, a, l, e, p, k, rhs, x, nrhs);
     return cudaGetLastError();
 }
 
@@ -66,20 +67,20 @@ static bool wsm_pack_pref()
 #define MODCHOL_CAT(a, b, c, d) MODCHOL_CAT2(a, b, c, d)
 cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT)(
     int n, long long batch, const double* a, double* l, double* e, unsigned long long* p, int* k,
-    int sms, cudaStream_t st)
+    const double* rhs, double* x, int nrhs, int sms, cudaStream_t st)
 {
     constexpr int A = MODCHOL_INST_ALGO;
     constexpr bool S = MODCHOL_INST_STRICT != 0;
     if (n <= 4)
-        return launch_wsm<A, 4, 1, S>(n, batch, a, l, e, p, k, sms, st);
+        return launch_wsm<A, 4, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 8)
-        return launch_wsm<A, 8, 1, S>(n, batch, a, l, e, p, k, sms, st);
+        return launch_wsm<A, 8, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 16)
-        return launch_wsm<A, 16, 1, S>(n, batch, a, l, e, p, k, sms, st);
+        return launch_wsm<A, 16, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 32)
-        return wsm_pack_pref() ? launch_wsm<A, 16, 2, S>(n, batch, a, l, e, p, k, sms, st)
-                               : launch_wsm<A, 32, 1, S>(n, batch, a, l, e, p, k, sms, st);
-    return launch_wsm<A, 32, 2, S>(n, batch, a, l, e, p, k, sms, st);
+        return wsm_pack_pref() ? launch_wsm<A, 16, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
+                               : launch_wsm<A, 32, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
+    return launch_wsm<A, 32, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
 }
 
 }  // namespace modchol

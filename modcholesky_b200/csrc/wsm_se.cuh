@@ -388,11 +388,66 @@ __device__ __forceinline__ unsigned wsm_group_mask(int grp)
         return ((1u << G) - 1u) << (grp * G);
 }
 
+// Fused consumer step: with the factor still in shared memory, solve
+// (A + E) x = b for nrhs right-hand sides:  P (A+E) P^T = L L^T with P[i, p_i] = 1, hence
+// L L^T (P x) = P b.  Lane = position: y_i = b[p_i]; forward substitution in axpy form over the
+// COLUMNS of L (conflict-free column reads), backward substitution in axpy form over its ROWS
+// (contiguous); x[p_i] = w_i.  Each step broadcasts one value and costs one LDS + one FMA per row.
+template <int G, int R>
+__device__ __forceinline__ void wsm_solve_in_place(unsigned mask, int n, unsigned wb,
+                                                   const unsigned (&tib)[R], const int (&row)[R],
+                                                   const bool (&rv)[R], const int (&perm)[R],
+                                                   const double* __restrict__ rhs,
+                                                   double* __restrict__ x, int nrhs)
+{
+    double rd[R];   // 1 / L_ii of this lane's positions
+#pragma unroll
+    for (int s = 0; s < R; ++s)
+        rd[s] = rv[s] ? ddiv(1.0, lds_f64(tib[s] + 8u * row[s])) : 0.0;
+    for (int r = 0; r < nrhs; ++r) {
+        double z[R], t[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            z[s] = rv[s] ? rhs[(size_t)r * n + perm[s]] : 0.0;
+        for (int j = 0; j < n; ++j) {   // L z = y
+#pragma unroll
+            for (int s = 0; s < R; ++s)
+                t[s] = dmul(z[s], rd[s]);
+            const double zj = wsm_bcast_row<G, R>(mask, t, j);
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                if (row[s] == j)
+                    z[s] = zj;
+                else if (rv[s] && row[s] > j)
+                    z[s] = __fma_rn(-lds_f64(tib[s] + 8u * j), zj, z[s]);
+            }
+        }
+        unsigned tjb = wb + 8u * (unsigned)tri(n - 1);
+        for (int j = n - 1; j >= 0; tjb -= 8u * (unsigned)j, --j) {   // L^T w = z
+#pragma unroll
+            for (int s = 0; s < R; ++s)
+                t[s] = dmul(z[s], rd[s]);
+            const double wj = wsm_bcast_row<G, R>(mask, t, j);
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                if (row[s] == j)
+                    z[s] = wj;
+                else if (row[s] < j)
+                    z[s] = __fma_rn(-lds_f64(tjb + 8u * row[s]), wj, z[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            if (rv[s])
+                x[(size_t)r * n + perm[s]] = z[s];
+    }
+}
+
 template <int kAlgo, int G, int R, bool kStrict, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
               double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
-              int* __restrict__ K)
+              int* __restrict__ K, const double* __restrict__ Bm, double* __restrict__ X, int nrhs)
 {
     extern __shared__ double sm[];
     // G lanes per matrix, 32 / G matrices per warp; every collective below is confined to the
@@ -804,15 +859,22 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         __syncwarp(mask);
 
         // ---- epilogue: L (strict upper explicitly zero), e un-permuted, p -------------------
-        wsm_store_lower<G, R>(L + (size_t)b * nn, n, wb, sub);
+        // (every output is optional: the fused solve may be all the caller wants)
+        if (L)
+            wsm_store_lower<G, R>(L + (size_t)b * nn, n, wb, sub);
 #pragma unroll
         for (int s = 0; s < R; ++s)
             if (rv[s]) {
-                E[(size_t)b * n + perm[s]] = ev[s];                       // se99.rs:194-198
-                P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
+                if (E)
+                    E[(size_t)b * n + perm[s]] = ev[s];                   // se99.rs:194-198
+                if (P)
+                    P[(size_t)b * n + row[s]] = (unsigned long long)perm[s];
             }
         if (K && sub == 0)
             K[b] = kstart;
+        if (X)
+            wsm_solve_in_place<G, R>(mask, n, wb, tib, row, rv, perm, Bm + (size_t)b * nrhs * n,
+                                     X + (size_t)b * nrhs * n, nrhs);
     }
 }
 

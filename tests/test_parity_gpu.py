@@ -274,6 +274,47 @@ def test_solve_batched_newton_step(torch_cuda, n):
     assert np.array_equal(x1, x[:, 0, :])
 
 
+@pytest.mark.parametrize("n", [1, 3, 8, 16, 31, 32, 48, 64, 100])
+def test_fused_factor_solve(oracle, torch_cuda, n):
+    """modchol_factor_solve_batched_f64: one call (one kernel for n <= 64) gives the x of
+    factor + solve, with every factor output optional and bit-identical when requested."""
+    torch = torch_cuda
+    b = 40
+    fam = "pd" if n < 3 else "wishart"
+    a = matgen.make(fam, 6000 + n, b, n)
+    rng = np.random.default_rng(n)
+    for algo in ALGOS:
+        for nrhs in (1, 3):
+            rhs = rng.standard_normal((b, nrhs, n))
+            for mode in ("strict", "fast"):
+                ad, rd = torch.from_numpy(a).cuda(), torch.from_numpy(rhs).cuda()
+                d = m.factor_batched(algo, ad, mode=mode)
+                x2 = m.solve_batched(d, rd).cpu().numpy()
+                x, df = m.factor_solve_batched(algo, ad, rd, mode=mode, return_factors=True)
+                x = x.cpu().numpy()
+                # the factors that come with it are the plain call's, bit for bit
+                assert torch.equal(df.l, d.l) and torch.equal(df.e, d.e) and torch.equal(df.p, d.p)
+                assert torch.equal(df.phase2_start, d.phase2_start)
+                # x without asking for the factors (NULL outputs) is the same x
+                x0 = m.factor_solve_batched(algo, ad, rd, mode=mode).cpu().numpy()
+                assert np.array_equal(x0, x)
+                e = d.e.cpu().numpy()
+                for i in range(b):
+                    ae = a[i] + np.diag(e[i])
+                    if not np.isfinite(ae).all():
+                        continue
+                    ref = np.linalg.solve(ae, rhs[i].T).T
+                    scale = np.abs(ref).max() * np.linalg.cond(ae)
+                    assert np.abs(x[i] - ref).max() <= 1e-13 * scale + 1e-300, (algo, n, mode, i)
+                    assert np.abs(x[i] - x2[i]).max() <= 1e-13 * scale + 1e-300, (algo, n, mode, i)
+            # host pointers, single right-hand side given as (batch, n)
+            xh = m.factor_solve_batched(algo, a, rhs[:, 0, :], mode="strict")
+            xdv = m.factor_solve_batched(algo, torch.from_numpy(a).cuda(),
+                                         torch.from_numpy(np.ascontiguousarray(rhs[:, 0, :])).cuda(),
+                                         mode="strict").cpu().numpy()
+            assert isinstance(xh, np.ndarray) and np.array_equal(xh, xdv)
+
+
 def test_host_pointer_path_matches_device_path(oracle, torch_cuda):
     """numpy in -> the C-ABI stages through the GPU in overlapped chunks; results identical."""
     for algo, n, b in (("se99", 32, 5000), ("gmw81", 17, 3000), ("se90", 64, 700)):
