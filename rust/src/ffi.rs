@@ -29,6 +29,11 @@ extern "C" {
         batch: i64, n: i32, nrhs: i32, l: *const f64, p: *const u64, b: *const f64, x: *mut f64,
         mem_kind: c_int, stream: *mut c_void,
     ) -> c_int;
+    pub fn modchol_factor_solve_batched_f64(
+        algo: c_int, mode: c_int, batch: i64, n: i32, nrhs: i32, a: *const f64, b: *const f64,
+        x: *mut f64, l: *mut f64, e: *mut f64, p: *mut u64, phase2_start: *mut i32,
+        mem_kind: c_int, stream: *mut c_void,
+    ) -> c_int;
     pub fn modchol_set_small_kernel_family(family: c_int) -> c_int;
     pub fn modchol_kernel_class(algo: c_int, mode: c_int, n: i32) -> *const c_char;
     pub fn modchol_launch_count() -> i64;
