@@ -20,6 +20,10 @@
 
 #include "warp_common.cuh"
 
+#ifndef MODCHOL_WSM_DMMA
+#define MODCHOL_WSM_DMMA 1   /* FAST mode: blocked rank-4 trailing update with DMMA (0 = off) */
+#endif
+
 namespace modchol {
 
 __host__ __device__ constexpr int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -388,6 +392,50 @@ __device__ __forceinline__ unsigned wsm_group_mask(int grp)
         return ((1u << G) - 1u) << (grp * G);
 }
 
+// FAST mode, one matrix per warp: blocked trailing update on the FP64 tensor pipe.  Every four
+// steps the finished columns [sbase, j) (at most four) are applied to the stored trailing block,
+//     W(i,k) -= sum_t W(i,t) W(k,t),   j <= k <= i < n,
+// as 8x8 tiles of one DMMA (mma.sync.m8n8k4.f64) each, so that the left-looking dot products
+// never span more than three columns: 8x fewer own-row loads and FMA issue slots for the same
+// flops.  Fragments: lane l holds A[l/4][l%4] = W(8 bi + l/4, sbase + l%4) (and the same element
+// pattern serves as B for column block bj), C[l/4][2 (l%4) + {0,1}].  The roundings differ from
+// the sequential order, hence FAST only.
+template <int kBlocks>
+__device__ __noinline__ void wsm_rank4_update_dmma(unsigned wb, int n, int j, int sbase, int lane)
+{
+    const int r8 = lane >> 2, c4 = lane & 3;
+    const int b0 = j >> 3, nb = (n + 7) >> 3, cnt = j - sbase;
+    double frag[kBlocks];
+#pragma unroll
+    for (int b = 0; b < kBlocks; ++b) {
+        const int rr = 8 * b + r8;
+        const bool in = b >= b0 && rr >= j && rr < n && c4 < cnt;
+        frag[b] = lds_f64_or_zero(in, wb + 8u * (unsigned)(tri(in ? rr : 0) + sbase + c4));
+    }
+#pragma unroll
+    for (int bi = 0; bi < kBlocks; ++bi) {
+        if (bi < b0 || bi >= nb)
+            continue;
+        const int i = 8 * bi + r8;
+        const unsigned ra = wb + 8u * (unsigned)tri(i < n ? i : 0);
+        const double na = -frag[bi];
+#pragma unroll
+        for (int bj = 0; bj <= bi; ++bj) {
+            if (bj < b0)
+                continue;
+            const int k0 = 8 * bj + 2 * c4, k1 = k0 + 1;
+            const bool p0 = i < n && k0 >= j && k0 <= i, p1 = i < n && k1 >= j && k1 <= i;
+            const double c0 = lds_f64_or_zero(p0, ra + 8u * (unsigned)k0);
+            const double c1 = lds_f64_or_zero(p1, ra + 8u * (unsigned)k1);
+            double d0, d1;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+                         : "=d"(d0), "=d"(d1) : "d"(na), "d"(frag[bj]), "d"(c0), "d"(c1));
+            sts_f64_if(p0, ra + 8u * (unsigned)k0, d0);
+            sts_f64_if(p1, ra + 8u * (unsigned)k1, d1);
+        }
+    }
+}
+
 // Fused consumer step: with the factor still in shared memory, solve
 // (A + E) x = b for nrhs right-hand sides:  P (A+E) P^T = L L^T with P[i, p_i] = 1, hence
 // L L^T (P x) = P b.  Lane = position: y_i = b[p_i]; forward substitution in axpy form over the
@@ -462,6 +510,10 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
     const unsigned lineb = scrb + 128u;                                  // 72-entry column line
     const size_t nn = (size_t)n * n;
     const long long nslots = (long long)gridDim.x * kWarps * kPack;
+    // blocked trailing update on the tensor pipe: FAST, one matrix per warp (mma.sync is warp-wide),
+    // one row per lane (measured: n=32 uniform +3 %, mixed-phase +16 % -- the phase switch then
+    // sweeps at most three columns; with two rows per lane, 32 < n <= 64, it loses 5-20 %)
+    constexpr bool kDmma = !kStrict && G == 32 && R == 1 && MODCHOL_WSM_DMMA;
 
     int row[R];
     unsigned tib[R];   // byte address of W(row, 0)
@@ -635,6 +687,13 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         int j = 0;
         unsigned tjb = wb;   // byte address of W(j,0), advanced with j
         for (; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+            if constexpr (kDmma) {
+                if (j - sbase == 4) {
+                    wsm_rank4_update_dmma<4 * R>(wb, n, j, sbase, lane);
+                    sbase = j;
+                    __syncwarp(mask);
+                }
+            }
             bool active[R];
 #pragma unroll
             for (int s = 0; s < R; ++s)
@@ -763,6 +822,13 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                     }
                 }
                 for (j = k0; j + 2 < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+                    if constexpr (kDmma) {
+                        if (j - sbase == 4) {
+                            wsm_rank4_update_dmma<4 * R>(wb, n, j, sbase, lane);
+                            sbase = j;
+                            __syncwarp(mask);
+                        }
+                    }
                     bool active[R];
 #pragma unroll
                     for (int s = 0; s < R; ++s)
