@@ -34,15 +34,12 @@ __device__ __forceinline__ void static_for(F&& f)
 // -0 is folded onto +0 (IEEE `>` treats them as equal, utils.rs:63).
 __device__ __forceinline__ void make_key(double v, int& khi, unsigned& klo)
 {
+    v = dadd(v, 0.0);   // -0.0 -> +0.0 (the two compare equal in the reference); one FP64 add
     const int hi = __double2hiint(v);
     const unsigned lo = (unsigned)__double2loint(v);
     const int mask = hi >> 31;
     khi = hi ^ (mask & 0x7fffffff);
     klo = lo ^ (unsigned)mask;
-    if (khi == -1 && klo == 0xffffffffu) {  // -0.0
-        khi = 0;
-        klo = 0u;
-    }
 }
 __device__ __forceinline__ double key_value(int khi, unsigned klo)
 {

@@ -505,7 +505,10 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
     const int sub = lane & (G - 1), grp = lane / G;
     const unsigned mask = wsm_group_mask<G>(grp);
     double* W = sm + (size_t)(wib * kPack + grp) * wstride;
-    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);          // byte address of W(0,0)
+    // byte address of W(0,0); pinned in a register (a volatile move stops the compiler from
+    // re-deriving it -- thread index arithmetic, cvta -- at every use under register pressure)
+    unsigned wb = (unsigned)__cvta_generic_to_shared(W);
+    asm volatile("mov.u32 %0, %0;" : "+r"(wb));
     const unsigned scrb = wb + 8u * (unsigned)((tri(n) + 1) & ~1);      // 16 doubles of scratch
     const unsigned lineb = scrb + 128u;                                  // 72-entry column line
     const size_t nn = (size_t)n * n;
@@ -523,6 +526,7 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         row[s] = sub + G * s;
         rv[s] = row[s] < n;
         tib[s] = wb + 8u * (unsigned)tri(rv[s] ? row[s] : 0);
+        asm volatile("mov.u32 %0, %0;" : "+r"(tib[s]));
     }
 
     for (long long b = ((long long)blockIdx.x * kWarps + wib) * kPack + grp; b < batch; b += nslots) {
