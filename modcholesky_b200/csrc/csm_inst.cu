@@ -10,7 +10,7 @@
 
 namespace modchol {
 
-template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks>
+template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks, bool kDmma = false>
 static cudaError_t launch_csm(int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
@@ -18,7 +18,7 @@ static cudaError_t launch_csm(int n, long long batch, const double* a, double* l
         if constexpr (kAlgo == kGMW81)
             return csm_gmw_kernel<kStrict, kThreads, kMinBlocks>;
         else
-            return csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks>;
+            return csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks, false, kDmma && !kStrict>;
     }();
     const size_t smem = csm_smem_bytes(n);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -47,7 +47,7 @@ static cudaError_t launch_csm_spill(int n, long long batch, const double* a, dou
         if constexpr (kAlgo == kGMW81)
             return csm_gmw_kernel<kStrict, kThreads, 1, true>;
         else
-            return csm_se_kernel<kAlgo, kStrict, kThreads, 1, true>;
+            return csm_se_kernel<kAlgo, kStrict, kThreads, 1, true, !kStrict>;
     }();
     int dev = 0, optin = 0;
     cudaError_t ce = cudaGetDevice(&dev);
@@ -82,10 +82,12 @@ cudaError_t MODCHOL_CAT(launch_csm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
 {
     constexpr int A = MODCHOL_INST_ALGO;
     constexpr bool S = MODCHOL_INST_STRICT != 0;
-    if (n <= 128)
+    if (n <= 112)
         return launch_csm<A, S, 128, 3>(n, batch, a, l, e, p, k, sms, st);
+    if (n <= 128)   // FAST: blocked DMMA trailing update from here on
+        return launch_csm<A, S, 128, 3, true>(n, batch, a, l, e, p, k, sms, st);
     if (n <= kCsmMaxN)
-        return launch_csm<A, S, 256, 1>(n, batch, a, l, e, p, k, sms, st);
+        return launch_csm<A, S, 256, 1, true>(n, batch, a, l, e, p, k, sms, st);
     return launch_csm_spill<A, S, 256>(n, batch, a, l, e, p, k, sms, st);
 }
 

@@ -205,7 +205,7 @@ __device__ __forceinline__ void csm_rank4_update_dmma(const CsmRows<kSpill>& row
     }
 }
 
-template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks, bool kSpill = false>
+template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks, bool kSpill = false, bool kDmma = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
               double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
@@ -365,9 +365,9 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             __syncthreads();
         };
         int sbase = 0;
-        // blocked DMMA trailing update: measured +3..27 % for n >= 128 (more with mixed phases),
-        // -10 % at n = 96 where six blocks per SM already hide the dot-product latency
-        const bool use_dmma = !kStrict && n > 112;
+        // blocked DMMA trailing update (kDmma, FAST only): measured +3..27 % for n >= 128 (more
+        // with mixed phases), -10 % at n = 96 where five blocks per SM already hide the
+        // dot-product latency and the extra registers cost one of them -- a separate instantiation
         // value of the row at position j, broadcast to the block (one sync)
         auto bcast_row = [&](double v, int j) -> double {
             double* D = sc.dbl + sc.buf * 8;
@@ -382,8 +382,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
         int j = 0;
         addr_t tjb = rows.row(0);
         for (; j < n; tjb = rows.next(tjb, j), ++j) {
-            if constexpr (!kStrict) {
-                if (use_dmma && j - sbase == 4) {
+            if constexpr (kDmma && !kStrict) {
+                if (j - sbase == 4) {
                     csm_rank4_update_dmma<kSpill>(rows, n, j, sbase, tid >> 5, nwarps, lane);
                     sbase = j;
                     __syncthreads();
@@ -484,8 +484,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                     }
                 }
                 for (j = k0; j + 2 < n; tjb = rows.next(tjb, j), ++j) {
-                    if constexpr (!kStrict) {
-                        if (use_dmma && j - sbase == 4) {
+                    if constexpr (kDmma && !kStrict) {
+                        if (j - sbase == 4) {
                             csm_rank4_update_dmma<kSpill>(rows, n, j, sbase, tid >> 5, nwarps, lane);
                             sbase = j;
                             __syncthreads();
