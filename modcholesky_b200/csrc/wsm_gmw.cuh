@@ -74,11 +74,14 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
 {
     extern __shared__ double sm[];
     constexpr int kPack = 32 / G;   // matrices per warp, G lanes each (see wsm_se.cuh)
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane));   // pinned in a register (see wsm_se.cuh)
+    const int wib = threadIdx.x >> 5;
     const int sub = lane & (G - 1), grp = lane / G;
     const unsigned mask = wsm_group_mask<G>(grp);
     double* W = sm + (size_t)(wib * kPack + grp) * wstride;
-    const unsigned wb = (unsigned)__cvta_generic_to_shared(W);
+    unsigned wb = (unsigned)__cvta_generic_to_shared(W);
+    asm volatile("mov.u32 %0, %0;" : "+r"(wb));
     const unsigned scrb = wb + 8u * (unsigned)((tri(n) + 1) & ~1);
     const unsigned lineb = scrb + 128u;
     const size_t nn = (size_t)n * n;
@@ -92,6 +95,7 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
         row[s] = sub + G * s;
         rv[s] = row[s] < n;
         tib[s] = wb + 8u * (unsigned)tri(rv[s] ? row[s] : 0);
+        asm volatile("mov.u32 %0, %0;" : "+r"(tib[s]));
     }
 
     for (long long b = ((long long)blockIdx.x * kWarps + wib) * kPack + grp; b < batch; b += nslots) {

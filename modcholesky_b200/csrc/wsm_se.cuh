@@ -501,7 +501,9 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
     // G lanes per matrix, 32 / G matrices per warp; every collective below is confined to the
     // group (member mask + shuffle width), so the groups of a warp may diverge freely
     constexpr int kPack = 32 / G;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane));   // pinned, see wb below
+    const int wib = threadIdx.x >> 5;
     const int sub = lane & (G - 1), grp = lane / G;
     const unsigned mask = wsm_group_mask<G>(grp);
     double* W = sm + (size_t)(wib * kPack + grp) * wstride;
