@@ -20,7 +20,7 @@ static cudaError_t launch_csm(int n, long long batch, const double* a, double* l
         else
             return csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks, false, kDmma && !kStrict>;
     }();
-    const size_t smem = csm_smem_bytes(n);
+    const size_t smem = csm_smem_bytes(n, 0, kDmma && !kStrict && kAlgo != kGMW81);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -54,10 +54,11 @@ static cudaError_t launch_csm_spill(int n, long long batch, const double* a, dou
     if (ce != cudaSuccess) return ce;
     ce = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (ce != cudaSuccess) return ce;
+    constexpr bool kPanel = !kStrict && kAlgo != kGMW81;   // the DMMA update's column panel
     int S = 1;
-    while (S < n && csm_smem_bytes(n, S) > (size_t)optin)
+    while (S < n && csm_smem_bytes(n, S, kPanel) > (size_t)optin)
         ++S;
-    const size_t smem = csm_smem_bytes(n, S);
+    const size_t smem = csm_smem_bytes(n, S, kPanel);
     if (smem > (size_t)optin) return cudaErrorInvalidValue;
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
@@ -86,7 +87,9 @@ cudaError_t MODCHOL_CAT(launch_csm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
         return launch_csm<A, S, 128, 3>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 128)   // FAST: blocked DMMA trailing update from here on
         return launch_csm<A, S, 128, 3, true>(n, batch, a, l, e, p, k, sms, st);
-    if (n <= kCsmMaxN)
+    // (the FAST SE kernels carry an 8 KB panel: they spill from n = 233 instead of 237)
+    const bool fits = csm_smem_bytes(n, 0, !S && A != kGMW81) <= (size_t)227 * 1024;
+    if (n <= kCsmMaxN && fits)
         return launch_csm<A, S, 256, 1, true>(n, batch, a, l, e, p, k, sms, st);
     return launch_csm_spill<A, S, 256>(n, batch, a, l, e, p, k, sms, st);
 }

@@ -165,43 +165,55 @@ struct CsmRows {
 
 // FAST mode: blocked trailing update on the FP64 tensor pipe (see wsm_rank4_update_dmma).  Every
 // four steps the finished columns [sbase, j) are applied to the stored trailing block as 8x8
-// tiles of one DMMA each, the tiles dealt round-robin to the warps of the block, so that the
-// per-thread left-looking dot product -- a serial chain of j dependent FMAs, the latency these
-// kernels are bound by -- never spans more than three columns.
+// tiles of one DMMA each, so that the per-thread left-looking dot product -- a serial chain of j
+// dependent FMAs -- never spans more than three columns.
+//   * the four columns are first copied into a compact shared-memory PANEL (row r at 4 r, rows
+//     < j and columns >= j - sbase zero, padded to a multiple of eight rows): the A and B
+//     fragments of every tile are plain 32-bit shared loads, and because finished rows
+//     contribute zeros, a tile may rewrite finished entries with their own value -- only the
+//     diagonal tiles (k <= i) and the last block row (i < n) need predicates;
+//   * each warp owns the block rows bi = b0 + warp, + nwarps, ...: one row address and one A
+//     fragment per block row, then 2 LDS + DMMA + 2 STS (+ 1 LDS for B) per tile.
+__host__ __device__ inline int csm_panel_doubles(int n) { return 4 * 8 * ((n + 7) >> 3); }
+
 template <bool kSpill>
 __device__ __forceinline__ void csm_rank4_update_dmma(const CsmRows<kSpill>& rows, int n, int j,
-                                                      int sbase, int warp, int nwarps, int lane)
+                                                      unsigned panelb, int warp, int nwarps, int lane)
 {
     using addr_t = typename CsmRows<kSpill>::addr_t;
     const int r8 = lane >> 2, c4 = lane & 3;
-    const int b0 = j >> 3, nb = (n + 7) >> 3, cnt = j - sbase;
-    int bi = b0, bj = b0 + warp;
-    for (;;) {
-        while (bj > bi) {
-            bj -= bi - b0 + 1;
-            ++bi;
+    const int b0 = j >> 3, nb = (n + 7) >> 3;
+    for (int bi = b0 + warp; bi < nb; bi += nwarps) {
+        const int i = 8 * bi + r8;
+        const bool iv = i < n;
+        const addr_t ra = rows.row(iv ? i : 0);
+        const double na = -lds_f64(panelb + 8u * (unsigned)(4 * i + c4));
+        const bool full = 8 * bi + 7 < n;
+        for (int bj = b0; bj <= bi; ++bj) {
+            const double fb = lds_f64(panelb + 8u * (unsigned)(4 * (8 * bj + r8) + c4));
+            const unsigned k0 = (unsigned)(8 * bj + 2 * c4);
+            double c0, c1, d0, d1;
+            if (bj < bi && full) {   // interior tile: no predicates (warp-uniform branch)
+                c0 = lds_f64(ra + 8u * k0);
+                c1 = lds_f64(ra + 8u * k0 + 8u);
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+                             : "=d"(d0), "=d"(d1) : "d"(na), "d"(fb), "d"(c0), "d"(c1));
+                sts_f64(ra + 8u * k0, d0);
+                sts_f64(ra + 8u * k0 + 8u, d1);
+            } else {
+                const bool p0 = iv && (int)k0 <= i, p1 = iv && (int)k0 + 1 <= i;
+                c0 = 0.0;
+                c1 = 0.0;
+                if (p0)
+                    c0 = lds_f64(ra + 8u * k0);
+                if (p1)
+                    c1 = lds_f64(ra + 8u * k0 + 8u);
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+                             : "=d"(d0), "=d"(d1) : "d"(na), "d"(fb), "d"(c0), "d"(c1));
+                sts_f64_if(p0, ra + 8u * k0, d0);
+                sts_f64_if(p1, ra + 8u * k0 + 8u, d1);
+            }
         }
-        if (bi >= nb)
-            break;
-        const int i = 8 * bi + r8, kr = 8 * bj + r8;
-        const addr_t ra = rows.row(i < n ? i : 0);
-        double fa = 0.0, fb = 0.0, c0 = 0.0, c1 = 0.0;
-        if (i >= j && i < n && c4 < cnt)
-            fa = lds_f64(ra + 8u * (unsigned)(sbase + c4));
-        if (kr >= j && kr < n && c4 < cnt)
-            fb = lds_f64(rows.row(kr) + 8u * (unsigned)(sbase + c4));
-        const int k0 = 8 * bj + 2 * c4, k1 = k0 + 1;
-        const bool p0 = i < n && k0 >= j && k0 <= i, p1 = i < n && k1 >= j && k1 <= i;
-        if (p0)
-            c0 = lds_f64(ra + 8u * (unsigned)k0);
-        if (p1)
-            c1 = lds_f64(ra + 8u * (unsigned)k1);
-        double d0, d1;
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
-                     : "=d"(d0), "=d"(d1) : "d"(-fa), "d"(fb), "d"(c0), "d"(c1));
-        sts_f64_if(p0, ra + 8u * (unsigned)k0, d0);
-        sts_f64_if(p1, ra + 8u * (unsigned)k1, d1);
-        bj += nwarps;
     }
 }
 
@@ -222,6 +234,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
     const int lpad = (n + 8 + 1) & ~1;
     CsmScratch sc = csm_scratch(linep + lpad);
     const unsigned wsh = (unsigned)__cvta_generic_to_shared(W);
+    // kDmma: the 4-column panel of the blocked update follows the scratch area
+    const unsigned panelb = wsh + 8u * (unsigned)(tpad + lpad + csm_scratch_doubles());
     if constexpr (kSpill) {
         rows.sbase = (unsigned long long)(size_t)W;
         rows.gb = (unsigned long long)(size_t)(spill + (size_t)blockIdx.x * rows.triS);
@@ -365,6 +379,23 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             __syncthreads();
         };
         int sbase = 0;
+        // fill the panel with columns [sbase, j) of the unfinished rows, run the tiles
+        auto blocked_update = [&](int j) {
+            const int prow = 8 * ((n + 7) >> 3);
+            if (tid < prow) {
+                const bool live = rv && row >= j;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    double v = 0.0;
+                    if (live && sbase + t < j)
+                        v = lds_f64(tib + 8u * (unsigned)(sbase + t));
+                    sts_f64(panelb + 8u * (unsigned)(4 * tid + t), v);
+                }
+            }
+            __syncthreads();
+            csm_rank4_update_dmma<kSpill>(rows, n, j, panelb, tid >> 5, nwarps, lane);
+            __syncthreads();
+        };
         // blocked DMMA trailing update (kDmma, FAST only): measured +3..27 % for n >= 128 (more
         // with mixed phases), -10 % at n = 96 where five blocks per SM already hide the
         // dot-product latency and the extra registers cost one of them -- a separate instantiation
@@ -384,9 +415,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
         for (; j < n; tjb = rows.next(tjb, j), ++j) {
             if constexpr (kDmma && !kStrict) {
                 if (j - sbase == 4) {
-                    csm_rank4_update_dmma<kSpill>(rows, n, j, sbase, tid >> 5, nwarps, lane);
+                    blocked_update(j);
                     sbase = j;
-                    __syncthreads();
                 }
             }
             const bool active = rv && row >= j;
@@ -486,9 +516,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                 for (j = k0; j + 2 < n; tjb = rows.next(tjb, j), ++j) {
                     if constexpr (kDmma && !kStrict) {
                         if (j - sbase == 4) {
-                            csm_rank4_update_dmma<kSpill>(rows, n, j, sbase, tid >> 5, nwarps, lane);
+                            blocked_update(j);
                             sbase = j;
-                            __syncthreads();
                         }
                     }
                     const bool active = rv && row >= j;
@@ -591,9 +620,10 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
 }
 
 // shared memory of one block when rows [0, S) are spilled (S = 0: nothing spilled)
-__host__ inline size_t csm_smem_bytes(int n, int S = 0)
+__host__ inline size_t csm_smem_bytes(int n, int S = 0, bool panel = false)
 {
-    return (size_t)(((tri(n) - tri(S) + 1) & ~1) + ((n + 8 + 1) & ~1) + csm_scratch_doubles()) *
+    return (size_t)(((tri(n) - tri(S) + 1) & ~1) + ((n + 8 + 1) & ~1) + csm_scratch_doubles() +
+                    (panel ? csm_panel_doubles(n) : 0)) *
            sizeof(double);
 }
 
