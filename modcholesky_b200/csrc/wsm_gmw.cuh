@@ -132,7 +132,70 @@ wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A
         const double rbeta = kStrict ? 0.0 : ddiv(1.0, beta);
 
         unsigned tjb = wb;
-        for (int j = 0; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+        if constexpr (!kStrict) {
+            // ---- FAST: the same factorisation in symmetric form --------------------------------
+            // W(i,s), s < j holds l~_is = c_is / sqrt(d_s) -- the FINAL L entry -- instead of c_is:
+            //   c_ij = a_ij - sum_s l~_is l~_js          (gmw81.rs:79-85 with l_js c_is = l~_js l~_is)
+            //   c_ii  runs in cd:  cd_i -= l~_ij^2       (gmw81.rs:104-109)
+            // so row j is read in place (no l_js line, no final scaling of the row), finished rows
+            // skip the dot product and, for one matrix per warp and one row per lane, the blocked
+            // DMMA update of wsm_se.cuh applies.  Same pivots, d_j, e_j up to rounding.
+            constexpr bool kDmma = G == 32 && R == 1 && MODCHOL_WSM_DMMA;
+            int sbase = 0;
+            for (int j = 0; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
+                if constexpr (kDmma) {
+                    if (j - sbase == 4) {
+                        wsm_rank4_update_dmma<4 * R>(wb, n, j, sbase, lane);
+                        sbase = j;
+                        __syncwarp(mask);
+                    }
+                }
+                bool active[R], below[R];
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    active[s] = rv[s] && row[s] >= j;
+                    below[s] = rv[s] && row[s] > j;
+                    av[s] = fabs(cd[s]);
+                }
+                double best;   // pivot on max |c_ii| (gmw81.rs:71-78)
+                const int m = wsm_argmax_first<R>(mask, av, active, row, j, best);
+                if (m != j)
+                    wsm_swap_positions<G, R>(mask, wb, scrb, tib, row, rv, sub, j, m, tjb, cd, dummy, perm);
+                // column j, its diagonal element included: c_jj comes from the same dot product as
+                // in the reference (gmw81.rs:83-85 with i = j), not from the running diagonal,
+                // whose different cancellation noise would show in E where E is tiny
+                double col[R], acol[R];
+                wsm_left_column<G, R, false, true>(j, tjb, sbase, tib, row, rv, col);
+                const double cjj = wsm_bcast_row<G, R>(mask, col, j);
+#pragma unroll
+                for (int s = 0; s < R; ++s)
+                    acol[s] = fabs(col[s]);
+                // theta = max_{i>j} |c_ij| (gmw81.rs:87-100), d_j (gmw81.rs:102)
+                const double theta = wsm_extreme<true, R>(mask, acol, below, 0.0, win);
+                const double tb = dmul(theta, rbeta);
+                const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);
+                double sq, y;
+                if (fast_range_ok(dj)) {
+                    y = rsqrt_normal(dj);
+                    sq = dmul(dj, y);
+                } else {
+                    sq = dsqrt(dj);
+                    y = ddiv(1.0, sq);
+                }
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    const double ls = dmul(col[s], y);
+                    sts_f64_if(below[s] || row[s] == j, below[s] ? tib[s] + 8u * j : tjb + 8u * j,
+                               below[s] ? ls : sq);
+                    if (below[s])
+                        cd[s] = __fma_rn(-ls, ls, cd[s]);
+                    if (row[s] == j)
+                        ev[s] = dsub(dj, cjj);                           // gmw81.rs:110
+                }
+                __syncwarp(mask);
+            }
+        }
+        for (int j = kStrict ? 0 : n; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
             // ---- pivot on max |c_ii| (gmw81.rs:71-78) ---------------------------------------
             bool active[R];
 #pragma unroll

@@ -392,6 +392,111 @@ __device__ __forceinline__ unsigned wsm_group_mask(int grp)
         return ((1u << G) - 1u) << (grp * G);
 }
 
+// LEFT-looking evaluation of the pivot column.  The reference updates the whole trailing
+// block at every step (l_ik -= l_ij l_kj, se90.rs:88-92); here columns >= j keep the
+// permuted INPUT and column j is brought up to date only now:
+//     col_i = a_ij - l_i,sbase l_j,sbase - ... - l_i,j-1 l_j,j-1      (in this order)
+// which applies exactly the same roundings in the same order as the right-looking
+// updates would have, with read-only shared-memory traffic (no store per element).
+// sbase = first column not yet applied to the stored trailing block (0, or the phase-2
+// start once the block has been materialised for the Gershgorin bounds).
+// kDiag: row j evaluates its own element too (col of row j = c_jj), for GMW81.
+template <int G, int R, bool kStrict, bool kDiag = false>
+__device__ __forceinline__ void wsm_left_column(int j, unsigned tjb, int sbase, const unsigned (&tib)[R],
+                                                const int (&row)[R], const bool (&rv)[R],
+                                                double (&col)[R])
+{
+    const int lo = kDiag ? j - 1 : j;   // rows > lo take part
+    // row j of L is contiguous at tjb (W(j, 0..j-1)) and is read by warp-wide broadcast
+    // loads, two columns per LDS.128 once (tjb + 8 t) is 16-byte aligned.  Finished rows
+    // (<= j) stay out of it: a lane whose rows are all finished skips the dot product
+    // (an idle half warp halves the wavefronts of every LDS.64 of the other half), and a
+    // slice s of rows that is finished in every lane is not evaluated at all.
+#pragma unroll
+    for (int s = 0; s < R; ++s)
+        col[s] = 0.0;
+    auto dot = [&](auto s0tag) {
+        constexpr int S0 = decltype(s0tag)::value;
+#pragma unroll
+        for (int s = S0; s < R; ++s)
+            col[s] = lds_f64(tib[s] + 8u * j);
+        unsigned rj = tjb + 8u * (unsigned)sbase;
+        unsigned ri[R];
+#pragma unroll
+        for (int s = S0; s < R; ++s)
+            ri[s] = tib[s] + 8u * (unsigned)sbase;
+        int left = j - sbase;
+        auto step1 = [&]() {
+            const double lj = lds_f64(rj);
+#pragma unroll
+            for (int s = S0; s < R; ++s)
+                col[s] = nmul_add<kStrict>(col[s], lds_f64(ri[s]), lj);
+        };
+        auto step2 = [&](unsigned o) {
+            const double2 l01 = lds_v2f64(rj + o);
+#pragma unroll
+            for (int s = S0; s < R; ++s) {
+                const double w0 = lds_f64(ri[s] + o), w1 = lds_f64(ri[s] + o + 8);
+                col[s] = nmul_add<kStrict>(col[s], w0, l01.x);
+                col[s] = nmul_add<kStrict>(col[s], w1, l01.y);
+            }
+        };
+        auto advance = [&](unsigned bytes) {
+            rj += bytes;
+#pragma unroll
+            for (int s = S0; s < R; ++s)
+                ri[s] += bytes;
+        };
+        if ((rj & 8u) && left > 0) {
+            step1();
+            advance(8);
+            --left;
+        }
+        for (; left >= 8; left -= 8) {
+            const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
+            const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
+            const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
+#pragma unroll
+            for (int s = S0; s < R; ++s) {
+                double w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    w[u] = lds_f64(ri[s] + 8u * u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    col[s] = nmul_add<kStrict>(col[s], w[u], lj[u]);
+            }
+            advance(64);
+        }
+        if (left & 4) {
+            step2(0);
+            step2(16);
+            advance(32);
+        }
+        if (left & 2) {
+            step2(0);
+            advance(16);
+        }
+        if (left & 1)
+            step1();
+    };
+    if constexpr (R == 1) {
+        if (rv[0] && row[0] > lo)
+            dot(std::integral_constant<int, 0>{});
+    } else {
+        if (lo >= G - 1) {   // slice 0 (rows < G) is finished in every lane
+            if (rv[R - 1] && row[R - 1] > lo)
+                dot(std::integral_constant<int, R - 1>{});
+        } else if (row[R - 1] > lo) {
+            dot(std::integral_constant<int, 0>{});
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < R; ++s)
+        if (!(rv[s] && row[s] > lo))
+            col[s] = 0.0;
+}
+
 // FAST mode, one matrix per warp: blocked trailing update on the FP64 tensor pipe.  Every four
 // steps the finished columns [sbase, j) (at most four) are applied to the stored trailing block,
 //     W(i,k) -= sum_t W(i,t) W(k,t),   j <= k <= i < n,
@@ -575,103 +680,8 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             }
             return fast;
         };
-        // LEFT-looking evaluation of the pivot column.  The reference updates the whole trailing
-        // block at every step (l_ik -= l_ij l_kj, se90.rs:88-92); here columns >= j keep the
-        // permuted INPUT and column j is brought up to date only now:
-        //     col_i = a_ij - l_i,sbase l_j,sbase - ... - l_i,j-1 l_j,j-1      (in this order)
-        // which applies exactly the same roundings in the same order as the right-looking
-        // updates would have, with read-only shared-memory traffic (no store per element).
-        // sbase = first column not yet applied to the stored trailing block (0, or the phase-2
-        // start once the block has been materialised for the Gershgorin bounds).
         auto left_column = [&](int j, unsigned tjb, int sbase, double (&col)[R]) {
-            // row j of L is contiguous at tjb (W(j, 0..j-1)) and is read by warp-wide broadcast
-            // loads, two columns per LDS.128 once (tjb + 8 t) is 16-byte aligned.  Finished rows
-            // (<= j) stay out of it: a lane whose rows are all finished skips the dot product
-            // (an idle half warp halves the wavefronts of every LDS.64 of the other half), and a
-            // slice s of rows that is finished in every lane is not evaluated at all.
-#pragma unroll
-            for (int s = 0; s < R; ++s)
-                col[s] = 0.0;
-            auto dot = [&](auto s0tag) {
-                constexpr int S0 = decltype(s0tag)::value;
-#pragma unroll
-                for (int s = S0; s < R; ++s)
-                    col[s] = lds_f64(tib[s] + 8u * j);
-                unsigned rj = tjb + 8u * (unsigned)sbase;
-                unsigned ri[R];
-#pragma unroll
-                for (int s = S0; s < R; ++s)
-                    ri[s] = tib[s] + 8u * (unsigned)sbase;
-                int left = j - sbase;
-                auto step1 = [&]() {
-                    const double lj = lds_f64(rj);
-#pragma unroll
-                    for (int s = S0; s < R; ++s)
-                        col[s] = nmul_add<kStrict>(col[s], lds_f64(ri[s]), lj);
-                };
-                auto step2 = [&](unsigned o) {
-                    const double2 l01 = lds_v2f64(rj + o);
-#pragma unroll
-                    for (int s = S0; s < R; ++s) {
-                        const double w0 = lds_f64(ri[s] + o), w1 = lds_f64(ri[s] + o + 8);
-                        col[s] = nmul_add<kStrict>(col[s], w0, l01.x);
-                        col[s] = nmul_add<kStrict>(col[s], w1, l01.y);
-                    }
-                };
-                auto advance = [&](unsigned bytes) {
-                    rj += bytes;
-#pragma unroll
-                    for (int s = S0; s < R; ++s)
-                        ri[s] += bytes;
-                };
-                if ((rj & 8u) && left > 0) {
-                    step1();
-                    advance(8);
-                    --left;
-                }
-                for (; left >= 8; left -= 8) {
-                    const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
-                    const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
-                    const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
-#pragma unroll
-                    for (int s = S0; s < R; ++s) {
-                        double w[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            w[u] = lds_f64(ri[s] + 8u * u);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            col[s] = nmul_add<kStrict>(col[s], w[u], lj[u]);
-                    }
-                    advance(64);
-                }
-                if (left & 4) {
-                    step2(0);
-                    step2(16);
-                    advance(32);
-                }
-                if (left & 2) {
-                    step2(0);
-                    advance(16);
-                }
-                if (left & 1)
-                    step1();
-            };
-            if constexpr (R == 1) {
-                if (rv[0] && row[0] > j)
-                    dot(std::integral_constant<int, 0>{});
-            } else {
-                if (j >= G - 1) {   // slice 0 (rows < G) is finished in every lane
-                    if (rv[R - 1] && row[R - 1] > j)
-                        dot(std::integral_constant<int, R - 1>{});
-                } else if (row[R - 1] > j) {
-                    dot(std::integral_constant<int, 0>{});
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < R; ++s)
-                if (!(rv[s] && row[s] > j))
-                    col[s] = 0.0;
+            wsm_left_column<G, R, kStrict>(j, tjb, sbase, tib, row, rv, col);
         };
         // write column j of L (se90.rs:84-87, se99.rs:96-99); the diagonal update of the
         // reference's trailing update (l_ii -= l_ij^2) is carried in dg

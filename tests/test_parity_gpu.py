@@ -58,9 +58,11 @@ def _assert_tolerance(tag, a, got, ref):
     cmp = firm & same_p
     escale = np.maximum(np.abs(ref.e).max(axis=1), 1e-300)
     anorm = np.maximum(np.abs(a).max(axis=(1, 2)), 1.0)
-    # E to 1e-10 relative (relative to ||E||; an E that is exactly 0 must be ~0 w.r.t. ||A||)
+    # E to 1e-10 relative to ||E||.  Where E is tiny (bench-style matrices: ||E|| ~ 1e-7 ||A||) every
+    # e_j = d_j - c_jj inherits the cancellation noise of c_jj = a_jj - sum(...), a few ulps of
+    # ||A|| in the reference itself, so agreement is required down to 1e-14 ||A|| (45 ulp), not below.
     de = np.abs(e - ref.e).max(axis=1)
-    bad = cmp & (de > TOL_E_REL * np.maximum(escale, 1e-6 * anorm))
+    bad = cmp & (de > TOL_E_REL * np.maximum(escale, 1e-4 * anorm))
     assert not bad.any(), f"{tag}: E differs beyond 1e-10 rel in {bad.sum()} matrices"
     # reconstruction for EVERY finite matrix, tie or not
     llt = l @ np.transpose(l, (0, 2, 1))
