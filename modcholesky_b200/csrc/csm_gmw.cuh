@@ -9,7 +9,7 @@
 
 namespace modchol {
 
-template <bool kStrict, int kThreads, int kMinBlocks, bool kSpill = false>
+template <bool kStrict, int kThreads, int kMinBlocks, bool kSpill = false, bool kDmma = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
                double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
@@ -34,6 +34,7 @@ csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
         rows.gb = 0;
     }
     const unsigned lineb = wsh + 8u * (unsigned)tpad;
+    const unsigned panelb = wsh + 8u * (unsigned)(tpad + lpad + csm_scratch_doubles());   // kDmma
     const int tid = threadIdx.x;
     const int nwarps = kThreads >> 5;
     const size_t nn = (size_t)n * n;
@@ -76,38 +77,84 @@ csm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
             dsqrt(fmax(fmax(diag_max, ddiv(off_max, dsqrt(dsub(dmul(nf, nf), 1.0)))), MODCHOL_EPS));
         const double rbeta = kStrict ? 0.0 : ddiv(1.0, beta);
 
+        // symmetric exchange of positions j < m (see wsm_swap_positions) + row scalars
+        auto swap_positions = [&](int j, int m, addr_t tjb) {
+            const addr_t tmb = rows.row(m);
+            const int i = row;
+            const bool act = rv && i != m;
+            addr_t a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
+            addr_t a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
+            if (!act) {
+                a1 = tib;
+                a2 = tib;
+            }
+            const double t1 = lds_f64(a1), t2 = lds_f64(a2);
+            if (i == j || i == m) {
+                double* q = sc.scal + (i == j ? 0 : 4);
+                q[0] = cd;
+                q[1] = (double)perm;
+            }
+            __syncthreads();
+            sts_f64_if(act, a1, t2);
+            sts_f64_if(act, a2, t1);
+            if (i == j || i == m) {
+                const double* q = sc.scal + (i == j ? 4 : 0);
+                cd = q[0];
+                perm = (int)q[1];
+            }
+            __syncthreads();
+        };
         addr_t tjb = rows.row(0);
-        for (int j = 0; j < n; tjb = rows.next(tjb, j), ++j) {
+        if constexpr (!kStrict) {
+            // ---- FAST: symmetric form (see wsm_gmw.cuh): W(i,s) = c_is / sqrt(d_s), the final L
+            // entry; row j read in place, finished rows skip the dot product, blocked DMMA update
+            int sbase = 0;
+            for (int j = 0; j < n; tjb = rows.next(tjb, j), ++j) {
+                if constexpr (kDmma) {
+                    if (j - sbase == 4) {
+                        csm_blocked_update<kSpill>(rows, n, j, sbase, panelb, tib, row, rv, tid, nwarps);
+                        sbase = j;
+                    }
+                }
+                const bool active = rv && row >= j, below = rv && row > j;
+                double best;   // pivot on max |c_ii| (gmw81.rs:71-78)
+                const int m = csm_argmax_first(sc, nwarps, fabs(cd), active, row, j, best);
+                if (m != j)
+                    swap_positions(j, m, tjb);
+                // column j with its diagonal element (c_jj from the same dot product, gmw81.rs:83-85)
+                const double col = csm_left_column<false, true, addr_t>(j, tjb, sbase, tib, row, rv);
+                double* D = sc.dbl + sc.buf * 8;
+                if (row == j)
+                    D[0] = col;
+                // theta = max_{i>j} |c_ij| (gmw81.rs:87-100); c_jj rides on the same barrier
+                const double theta = csm_extreme<true>(sc, nwarps, fabs(col), below, 0.0, win);
+                const double cjj = D[0];
+                const double tb = dmul(theta, rbeta);
+                const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
+                double sq, y;
+                if (fast_range_ok(dj)) {
+                    y = rsqrt_normal(dj);
+                    sq = dmul(dj, y);
+                } else {
+                    sq = dsqrt(dj);
+                    y = ddiv(1.0, sq);
+                }
+                const double ls = dmul(col, y);
+                sts_f64_if(below || row == j, below ? tib + 8u * j : tjb + 8u * j, below ? ls : sq);
+                if (below)
+                    cd = __fma_rn(-ls, ls, cd);
+                if (row == j)
+                    ev = dsub(dj, cjj);                                  // gmw81.rs:110
+                __syncthreads();
+            }
+        }
+        for (int j = kStrict ? 0 : n; j < n; tjb = rows.next(tjb, j), ++j) {
             // ---- pivot on max |c_ii| (gmw81.rs:71-78) ---------------------------------------
             const bool active = rv && row >= j;
             double best;
             const int m = csm_argmax_first(sc, nwarps, fabs(cd), active, row, j, best);
-            if (m != j) {  // symmetric exchange of positions j < m (see wsm_swap_positions)
-                const addr_t tmb = rows.row(m);
-                const int i = row;
-                const bool act = rv && i != m;
-                addr_t a1 = (i <= j) ? tjb + 8u * i : tib + 8u * j;
-                addr_t a2 = (i == j) ? tmb + 8u * m : ((i < m) ? tmb + 8u * i : tib + 8u * m);
-                if (!act) {
-                    a1 = tib;
-                    a2 = tib;
-                }
-                const double t1 = lds_f64(a1), t2 = lds_f64(a2);
-                if (i == j || i == m) {
-                    double* q = sc.scal + (i == j ? 0 : 4);
-                    q[0] = cd;
-                    q[1] = (double)perm;
-                }
-                __syncthreads();
-                sts_f64_if(act, a1, t2);
-                sts_f64_if(act, a2, t1);
-                if (i == j || i == m) {
-                    const double* q = sc.scal + (i == j ? 4 : 0);
-                    cd = q[0];
-                    perm = (int)q[1];
-                }
-                __syncthreads();
-            }
+            if (m != j)
+                swap_positions(j, m, tjb);
             // ---- l_js = c_js / d_s, s < j (gmw81.rs:79-81): thread s owns d_s ---------------
             double ljs = 0.0;
             if (rv && row < j) {

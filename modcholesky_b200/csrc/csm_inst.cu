@@ -16,11 +16,11 @@ static cudaError_t launch_csm(int n, long long batch, const double* a, double* l
 {
     auto kern = [] {
         if constexpr (kAlgo == kGMW81)
-            return csm_gmw_kernel<kStrict, kThreads, kMinBlocks>;
+            return csm_gmw_kernel<kStrict, kThreads, kMinBlocks, false, kDmma && !kStrict>;
         else
             return csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks, false, kDmma && !kStrict>;
     }();
-    const size_t smem = csm_smem_bytes(n, 0, kDmma && !kStrict && kAlgo != kGMW81);
+    const size_t smem = csm_smem_bytes(n, 0, kDmma && !kStrict);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -45,7 +45,7 @@ static cudaError_t launch_csm_spill(int n, long long batch, const double* a, dou
 {
     auto kern = [] {
         if constexpr (kAlgo == kGMW81)
-            return csm_gmw_kernel<kStrict, kThreads, 1, true>;
+            return csm_gmw_kernel<kStrict, kThreads, 1, true, !kStrict>;
         else
             return csm_se_kernel<kAlgo, kStrict, kThreads, 1, true, !kStrict>;
     }();
@@ -54,7 +54,7 @@ static cudaError_t launch_csm_spill(int n, long long batch, const double* a, dou
     if (ce != cudaSuccess) return ce;
     ce = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (ce != cudaSuccess) return ce;
-    constexpr bool kPanel = !kStrict && kAlgo != kGMW81;   // the DMMA update's column panel
+    constexpr bool kPanel = !kStrict;   // the DMMA update's column panel
     int S = 1;
     while (S < n && csm_smem_bytes(n, S, kPanel) > (size_t)optin)
         ++S;
@@ -87,8 +87,8 @@ cudaError_t MODCHOL_CAT(launch_csm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
         return launch_csm<A, S, 128, 3>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 128)   // FAST: blocked DMMA trailing update from here on
         return launch_csm<A, S, 128, 3, true>(n, batch, a, l, e, p, k, sms, st);
-    // (the FAST SE kernels carry an 8 KB panel: they spill from n = 233 instead of 237)
-    const bool fits = csm_smem_bytes(n, 0, !S && A != kGMW81) <= (size_t)227 * 1024;
+    // (the FAST kernels carry an 8 KB panel: they spill from n = 233 instead of 237)
+    const bool fits = csm_smem_bytes(n, 0, !S) <= (size_t)227 * 1024;
     if (n <= kCsmMaxN && fits)
         return launch_csm<A, S, 256, 1, true>(n, batch, a, l, e, p, k, sms, st);
     return launch_csm_spill<A, S, 256>(n, batch, a, l, e, p, k, sms, st);

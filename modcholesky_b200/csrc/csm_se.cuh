@@ -217,6 +217,83 @@ __device__ __forceinline__ void csm_rank4_update_dmma(const CsmRows<kSpill>& row
     }
 }
 
+// LEFT-looking evaluation of the pivot column (see wsm_se.cuh): columns >= j keep the
+// permuted input until column j is needed,
+//     col_i = a_ij - l_i,sbase l_j,sbase - ... - l_i,j-1 l_j,j-1      (in this order),
+// the same roundings in the same order as the reference's right-looking updates, with
+// read-only shared-memory traffic.  Two __syncthreads (line fill, line release).
+// kDiag: the thread at position j evaluates its own diagonal element too (GMW81's c_jj).
+template <bool kStrict, bool kDiag, typename addr_t>
+__device__ __forceinline__ double csm_left_column(int j, addr_t tjb, int sbase, addr_t tib, int row,
+                                                  bool rv)
+{
+    // row j of L is read in place (contiguous at tjb, block-wide broadcast loads, LDS.128
+    // once 16-byte aligned); finished rows skip the dot product.  No barrier is needed
+    // here: rows j and the thread's own row were last written before the swap's barrier,
+    // and every consumer of the result goes through a block collective first.
+    double col = 0.0;
+    if (rv && row > (kDiag ? j - 1 : j)) {
+        col = lds_f64(tib + 8u * j);
+        addr_t rj = tjb + 8u * (unsigned)sbase, ri = tib + 8u * (unsigned)sbase;
+        int left = j - sbase;
+        if ((rj & 8u) && left > 0) {
+            col = nmul_add<kStrict>(col, lds_f64(ri), lds_f64(rj));
+            rj += 8;
+            ri += 8;
+            --left;
+        }
+        for (; left >= 8; left -= 8) {
+            const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
+            const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
+            const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
+            double w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                w[u] = lds_f64(ri + 8u * u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                col = nmul_add<kStrict>(col, w[u], lj[u]);
+            rj += 64;
+            ri += 64;
+        }
+        for (; left >= 2; left -= 2) {
+            const double2 l01 = lds_v2f64(rj);
+            const double w0 = lds_f64(ri), w1 = lds_f64(ri + 8);
+            col = nmul_add<kStrict>(col, w0, l01.x);
+            col = nmul_add<kStrict>(col, w1, l01.y);
+            rj += 16;
+            ri += 16;
+        }
+        if (left)
+            col = nmul_add<kStrict>(col, lds_f64(ri), lds_f64(rj));
+    }
+    return col;
+}
+
+// FAST: the blocked update of the stored trailing block with columns [sbase, j) (j - sbase = 4):
+// every live row copies its four entries into the panel, then the DMMA tiles run.
+template <bool kSpill>
+__device__ __forceinline__ void csm_blocked_update(const CsmRows<kSpill>& rows, int n, int j, int sbase,
+                                                   unsigned panelb,
+                                                   typename CsmRows<kSpill>::addr_t tib, int row,
+                                                   bool rv, int tid, int nwarps)
+{
+    const int prow = 8 * ((n + 7) >> 3);
+    if (tid < prow) {
+        const bool live = rv && row >= j;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            double v = 0.0;
+            if (live && sbase + t < j)
+                v = lds_f64(tib + 8u * (unsigned)(sbase + t));
+            sts_f64(panelb + 8u * (unsigned)(4 * tid + t), v);
+        }
+    }
+    __syncthreads();
+    csm_rank4_update_dmma<kSpill>(rows, n, j, panelb, tid >> 5, nwarps, tid & 31);
+    __syncthreads();
+}
+
 template <int kAlgo, bool kStrict, int kThreads, int kMinBlocks, bool kSpill = false, bool kDmma = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
@@ -322,53 +399,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             }
             return fast;
         };
-        // LEFT-looking evaluation of the pivot column (see wsm_se.cuh): columns >= j keep the
-        // permuted input until column j is needed,
-        //     col_i = a_ij - l_i,sbase l_j,sbase - ... - l_i,j-1 l_j,j-1      (in this order),
-        // the same roundings in the same order as the reference's right-looking updates, with
-        // read-only shared-memory traffic.  Two __syncthreads (line fill, line release).
         auto left_column = [&](int j, addr_t tjb, int sbase) -> double {
-            // row j of L is read in place (contiguous at tjb, block-wide broadcast loads, LDS.128
-            // once 16-byte aligned); finished rows skip the dot product.  No barrier is needed
-            // here: rows j and the thread's own row were last written before the swap's barrier,
-            // and every consumer of the result goes through a block collective first.
-            double col = 0.0;
-            if (rv && row > j) {
-                col = lds_f64(tib + 8u * j);
-                addr_t rj = tjb + 8u * (unsigned)sbase, ri = tib + 8u * (unsigned)sbase;
-                int left = j - sbase;
-                if ((rj & 8u) && left > 0) {
-                    col = nmul_add<kStrict>(col, lds_f64(ri), lds_f64(rj));
-                    rj += 8;
-                    ri += 8;
-                    --left;
-                }
-                for (; left >= 8; left -= 8) {
-                    const double2 l01 = lds_v2f64(rj), l23 = lds_v2f64(rj + 16);
-                    const double2 l45 = lds_v2f64(rj + 32), l67 = lds_v2f64(rj + 48);
-                    const double lj[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
-                    double w[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        w[u] = lds_f64(ri + 8u * u);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        col = nmul_add<kStrict>(col, w[u], lj[u]);
-                    rj += 64;
-                    ri += 64;
-                }
-                for (; left >= 2; left -= 2) {
-                    const double2 l01 = lds_v2f64(rj);
-                    const double w0 = lds_f64(ri), w1 = lds_f64(ri + 8);
-                    col = nmul_add<kStrict>(col, w0, l01.x);
-                    col = nmul_add<kStrict>(col, w1, l01.y);
-                    rj += 16;
-                    ri += 16;
-                }
-                if (left)
-                    col = nmul_add<kStrict>(col, lds_f64(ri), lds_f64(rj));
-            }
-            return col;
+            return csm_left_column<kStrict, false, addr_t>(j, tjb, sbase, tib, row, rv);
         };
         // write column j of L (se90.rs:84-87, se99.rs:96-99); the diagonal update is carried in dg
         auto eliminate = [&](int j, addr_t tjb, double sq, double cs, double dg_new) {
@@ -379,22 +411,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             __syncthreads();
         };
         int sbase = 0;
-        // fill the panel with columns [sbase, j) of the unfinished rows, run the tiles
         auto blocked_update = [&](int j) {
-            const int prow = 8 * ((n + 7) >> 3);
-            if (tid < prow) {
-                const bool live = rv && row >= j;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    double v = 0.0;
-                    if (live && sbase + t < j)
-                        v = lds_f64(tib + 8u * (unsigned)(sbase + t));
-                    sts_f64(panelb + 8u * (unsigned)(4 * tid + t), v);
-                }
-            }
-            __syncthreads();
-            csm_rank4_update_dmma<kSpill>(rows, n, j, panelb, tid >> 5, nwarps, lane);
-            __syncthreads();
+            csm_blocked_update<kSpill>(rows, n, j, sbase, panelb, tib, row, rv, tid, nwarps);
         };
         // blocked DMMA trailing update (kDmma, FAST only): measured +3..27 % for n >= 128 (more
         // with mixed phases), -10 % at n = 96 where five blocks per SM already hide the
