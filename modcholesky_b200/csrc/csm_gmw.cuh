@@ -1,8 +1,9 @@
 // csm_gmw.cuh -- GMW81 (gmw81.rs:39-134), one thread block per matrix, packed lower triangle in
 // shared memory, thread = permuted position.  Block-level sibling of wsm_gmw.cuh (same storage
 // conventions: W(i,s) = c_is for s < j and i >= j, final L entries for finished rows, untouched
-// input for s >= j; LEFT-looking dot products in ndarray order) with the two-level collectives of
-// csm_se.cuh.  64 < n <= 236.
+// input for s >= j; LEFT-looking dot products in ndarray order; FAST: the symmetric form with
+// W(i,s) = c_is / sqrt(d_s)) with the two-level collectives of csm_se.cuh.  64 < n <= 256
+// (kSpill above 236).
 #pragma once
 #include "csm_se.cuh"
 #include "wsm_gmw.cuh"

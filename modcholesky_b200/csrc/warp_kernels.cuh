@@ -67,7 +67,7 @@ inline cudaError_t launch_wsm_kernel(int algo, int mode, int n, long long batch,
     return cudaErrorNotSupported;
 }
 
-// block-per-matrix packed shared-memory kernels (csm_se.cuh, csm_gmw.cuh), 64 < n <= 236;
+// block-per-matrix packed shared-memory kernels (csm_se.cuh, csm_gmw.cuh), 64 < n <= 256;
 // defined in csm_inst.cu
 #define MODCHOL_DECL_CSM(A, S)                                                                   \
     cudaError_t launch_csm_a##A##_s##S(int n, long long batch, const double* a, double* l,       \

@@ -1,5 +1,6 @@
 // warp_se.cuh -- SE90 / SE99 (se90.rs:38-181, se99.rs:35-201), one warp per matrix, the
-// matrix resident in registers for the whole factorisation (n <= NMAX <= 32).
+// matrix resident in registers for the whole factorisation (n <= NMAX <= 32).  The ALTERNATE
+// small-n family (modchol_set_small_kernel_family(1)); the default is wsm_se.cuh.
 // See warp_common.cuh for the data layout.  HBM traffic per matrix is exactly the
 // algorithmic 16 n^2 + 16 n bytes (+4 for phase2_start): A is read once with coalesced
 // row-of-the-batch loads, L / e / p are written once.

@@ -1,7 +1,7 @@
 // wsm_gmw.cuh -- GMW81 (gmw81.rs:39-134) with the matrix resident in shared memory: one warp per
 // matrix, packed lower triangle, lane = permuted position, R rows per lane (n <= 32 R).
-// Same storage and swap as wsm_se.cuh; LEFT-looking like the reference so that STRICT mode
-// reproduces every rounding:
+// Same storage and swap as wsm_se.cuh.  STRICT: LEFT-looking like the reference so that every
+// rounding is reproduced (FAST uses the symmetric form described at its loop below):
 //   W(i,s), s <  j : c_is for the rows i >= j still to be eliminated (gmw81.rs:84); for a
 //                    finished row i < j the FINAL L entry l_is * sqrt(d_s) (gmw81.rs:112-125)
 //   W(i,s), s >= j : the permuted input (never modified by the reference either)

@@ -1,20 +1,23 @@
-// wsm_se.cuh -- SE90 / SE99 with the matrix resident in SHARED memory: one warp per matrix,
-// packed lower triangle, lane = permuted position (row), R rows per lane (n <= 32 R).
+// wsm_se.cuh -- SE90 / SE99 (se90.rs:38-181, se99.rs:35-201) with the matrix resident in SHARED
+// memory: G = 4/8/16/32 lanes per matrix (32 / G matrices per warp), packed lower triangle,
+// lane = permuted position (row), R rows per lane (n <= G R).  The hot path for every n <= 64.
 //
-// Why a second small-n family next to the register-resident kernels (warp_se.cuh):
-//   * the register kernels keep full rows (the symmetric half is redundant) and the 32x32
-//     matrix takes 64 of ~124 registers, which caps an SM at 16 matrices in flight; every warp
-//     is latency bound on its own dependent chain (profiles/r01_notes.md).  Here a matrix costs
-//     n(n+1)/2 doubles of shared memory (4.2 KB at n = 32, 16.6 KB at n = 64) and ~50
-//     registers per lane, so 3x more matrices are in flight per SM.
-//   * rows live at their permuted POSITION, so the symmetric row/column swap
-//     (utils.rs:30-49) is four shared-memory accesses per lane, all indexing is run-time
-//     (no per-j code specialisation, 10x less SASS), and only the lower triangle is updated.
-//   * packed row-major lower storage, element (i,k) at T(i)+k with T(i) = i(i+1)/2: the
-//     triangular numbers are a permutation modulo 16 on every aligned run of 16 rows, so a
-//     column access by 32 lanes (8-byte elements, 16 lanes per wavefront) is conflict free.
+//   * packed row-major lower storage, element (i,k) at T(i)+k with T(i) = i(i+1)/2: 4.2 KB at
+//     n = 32, 16.6 KB at n = 64 and ~60 registers per lane, so an SM holds 32 warps (the
+//     register-resident family, warp_se.cuh, holds 16 and is latency bound).  The triangular
+//     numbers are a permutation modulo 16 on every aligned run of 16 rows, so a column access
+//     by 32 lanes (8-byte elements, 16 lanes per wavefront) is conflict free;
+//   * rows live at their permuted POSITION, so the symmetric row/column swap (utils.rs:30-49)
+//     is two loads and two predicated stores per lane and all indexing is run-time (no per-j
+//     code specialisation);
+//   * LEFT-looking: columns >= j keep the permuted input and column j is brought up to date when
+//     it becomes the pivot column (wsm_left_column) -- the same roundings in the same order as
+//     the reference's right-looking update; FAST mode with one matrix per warp additionally
+//     applies the finished columns in blocks of four on the FP64 tensor pipe
+//     (wsm_rank4_update_dmma);
+//   * explicit 32-bit shared addressing, predicated single-instruction stores.
 // Only the lower triangle of A is read (A symmetric), so DRAM reads drop below the
-// algorithmic 8 n^2 bytes.
+// algorithmic 8 n^2 bytes.  Measurements and the optimisation log: profiles/r01_notes.md.
 #pragma once
 #include <type_traits>
 

@@ -60,6 +60,24 @@ def test_bad_arguments_are_rejected_before_any_cuda_work():
     assert b"null" in L.modchol_last_error()
 
 
+def test_fused_factor_solve_rejects_bad_arguments():
+    L = m.lib()
+    a = np.zeros((1, 2, 2))
+    b = np.zeros((1, 1, 2))
+    pa, pb = a.ctypes.data, b.ctypes.data
+    f = L.modchol_factor_solve_batched_f64
+    assert f(2, 0, 1, 2, 0, pa, pb, pb, None, None, None, None, 0, None) == -1     # nrhs < 1
+    assert f(2, 0, 1, 2, 1, pa, None, pb, None, None, None, None, 0, None) == -1   # no right-hand side
+    assert f(2, 0, 1, 2, 1, pa, pb, None, None, None, None, None, 0, None) == -1   # no x
+    assert f(9, 0, 1, 2, 1, pa, pb, pb, None, None, None, None, 0, None) == -1     # algo
+    assert f(2, 0, 1, 2, 1, pa, pb, pb, None, None, None, None, 7, None) == -1     # mem_kind
+    assert f(2, 0, 1, 5000, 1, pa, pb, pb, None, None, None, None, 0, None) == -3  # > MAX_N
+    if m.device_count() == 0:   # every output optional, but still no CPU path
+        assert f(2, 0, 1, 2, 1, pa, pb, pb, None, None, None, None, 0, None) == -4
+    with pytest.raises(ValueError):
+        m.factor_solve_batched("se99", np.zeros((2, 3, 3)), np.zeros((2, 4)))
+
+
 def test_non_square_raises_like_the_reference_assert():
     with pytest.raises(m.NotSquareError):
         m.Array2(np.zeros((2, 3))).mod_cholesky_se99()
