@@ -430,6 +430,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
         // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
         int j = 0;
         addr_t tjb = rows.row(0);
+        bool have_dmin = false;
+        double dmin_carry = 0.0;
         for (; j < n; tjb = rows.next(tjb, j), ++j) {
             if constexpr (kDmma && !kStrict) {
                 if (j - sbase == 4) {
@@ -441,7 +443,10 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             double dmax;
             const int m = csm_argmax_first(sc, nwarps, dg, active, row, j, dmax);
             if (kAlgo == kSE99) {  // se99.rs:62-73
-                const double dmin = csm_extreme<false>(sc, nwarps, dg, active, INFINITY, win);
+                // FAST: the previous step's look-ahead minimum is this minimum (see wsm_se.cuh)
+                const double dmin = (!kStrict && have_dmin)
+                                        ? dmin_carry
+                                        : csm_extreme<false>(sc, nwarps, dg, active, INFINITY, win);
                 if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
                     kstart = j;
                     break;
@@ -458,6 +463,8 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             const double dg_new = nmul_add<kStrict>(dg, cs, cs);
             const double nv = fast ? dg_new : dsub(dg, ddiv(dmul(col, col), piv));
             const double la = csm_extreme<false>(sc, nwarps, nv, below, INFINITY, win);
+            have_dmin = fast;
+            dmin_carry = la;
             const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
             if (la < thresh) {
                 kstart = j;

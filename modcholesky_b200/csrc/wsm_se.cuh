@@ -705,6 +705,8 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
         // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) --------------------------------------
         int j = 0;
         unsigned tjb = wb;   // byte address of W(j,0), advanced with j
+        bool have_dmin = false;
+        double dmin_carry = 0.0;
         for (; j < n; tjb += 8u * (unsigned)(j + 1), ++j) {
             if constexpr (kDmma) {
                 if (j - sbase == 4) {
@@ -720,7 +722,11 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             double dmax;
             const int m = wsm_argmax_first<R>(mask, dg, active, row, j, dmax);
             if (kAlgo == kSE99) {  // se99.rs:62-73, before the pivot is applied
-                const double dmin = wsm_extreme<false, R>(mask, dg, active, INFINITY, win);
+                // FAST: the minimum of the diagonal over rows >= j IS the previous step's
+                // look-ahead minimum (same rows, same values) -- no second reduction
+                const double dmin = (!kStrict && have_dmin)
+                                        ? dmin_carry
+                                        : wsm_extreme<false, R>(mask, dg, active, INFINITY, win);
                 if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax)) {
                     kstart = j;
                     break;
@@ -745,6 +751,8 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                 nv[s] = fast ? dg_new[s] : dsub(dg[s], ddiv(dmul(col, col), piv));
             }
             const double la = wsm_extreme<false, R>(mask, nv, below, INFINITY, win);
+            have_dmin = fast;
+            dmin_carry = la;
             const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
             if (la < thresh) {  // the pivot at j stays applied (se99.rs:90-93)
                 kstart = j;
