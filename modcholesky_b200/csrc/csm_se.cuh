@@ -454,7 +454,9 @@ csm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             }
             if (m != j)
                 swap_positions(j, m, tjb);
-            const double piv = bcast_row(dg, j);
+            // FAST: a winner other than the head is a non-NaN maximum and its value is the pivot
+            // (saves the broadcast and its barrier); otherwise read the diagonal at position j
+            const double piv = (!kStrict && m != j) ? dmax : bcast_row(dg, j);
             double sq, y, inv_piv;
             const bool fast = scale(piv, sq, y, inv_piv);
             const bool below = rv && row > j;

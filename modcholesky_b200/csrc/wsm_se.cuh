@@ -734,7 +734,8 @@ wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
             }
             if (m != j)
                 swap_positions(j, m, tjb, false);
-            const double piv = bcast_row(dg, j);
+            // FAST: a winner other than the head is a non-NaN maximum and its value is the pivot
+            const double piv = (!kStrict && m != j) ? dmax : bcast_row(dg, j);
             double colv[R];
             left_column(j, tjb, sbase, colv);
             double sq, y, inv_piv;
