@@ -236,7 +236,7 @@ def main():
     ms_per_step = ms / args.steps
     value = world * batch / (ms_per_step * 1e-3)
     other = "strict" if args.mode == "fast" else "fast"
-    ms_o, _, _, _ = timed(other, max(2, args.steps // 2), 1)
+    ms_o, _, _, _ = timed(other, max(2, args.steps // 2), 3)
     value_other = world * batch / (ms_o / max(2, args.steps // 2) * 1e-3)
 
     # parity spot check against the oracle on rank 0 (checker only; not timed)
