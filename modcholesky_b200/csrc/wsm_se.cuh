@@ -355,7 +355,9 @@ __device__ __forceinline__ void wsm_swap_positions(unsigned mask, unsigned wb, u
             }
         }
     }
-    __syncwarp(mask);
+    if constexpr (R > 1)
+        __syncwarp(mask);   // scratch written above is read below (R == 1: every lane exchanges
+                            // its own disjoint pair of elements, no barrier needed before the stores)
 #pragma unroll
     for (int s = 0; s < R; ++s) {
         sts_f64_if(act[s], a1[s], t2[s]);
