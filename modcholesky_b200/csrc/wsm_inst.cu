@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "warp_kernels.cuh"
+#include "wip_kernels.cuh"
 #include "wsm_gmw.cuh"
 #include "wsm_se.cuh"
 
@@ -53,6 +54,47 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
     return cudaGetLastError();
 }
 
+// FAST mode, 16 < n <= 32, no fused solve: the implicit-pivoting kernels (wip_kernels.cuh).
+// The launch attributes and the occupancy are queried once per instantiation and device.
+#ifndef MODCHOL_WIP_MINB
+#define MODCHOL_WIP_MINB 8
+#endif
+template <int kAlgo, int NB>
+static cudaError_t launch_wip(int n, long long batch, const double* a, double* l, double* e,
+                              unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    constexpr int kWarps = 4;
+    auto kern = wip_kernel<kAlgo, NB, kWarps, MODCHOL_WIP_MINB>;
+    constexpr size_t smem = (size_t)kWarps * kWipDoubles * sizeof(double);
+    static int occ_dev[64];   // resident blocks per SM, 0 = not yet queried on that device
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    int occ = dev < 64 ? occ_dev[dev] : 0;
+    if (occ == 0) {
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+        ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared);
+        if (ce != cudaSuccess) return ce;
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem);
+        if (ce != cudaSuccess) return ce;
+        if (occ < 1) occ = 1;
+        if (dev < 64) occ_dev[dev] = occ;   // benign race: every writer stores the same value
+    }
+    long long blocks = (batch + kWarps - 1) / kWarps;
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
+    kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    return cudaGetLastError();
+}
+
+static bool wip_enabled()
+{
+    const char* v = getenv("MODCHOL_WIP");
+    return !(v && v[0] == '0');
+}
+
 // 16 < n <= 32 can also run two matrices per warp (16 lanes x 2 rows each): 11 % fewer
 // instructions per matrix and +4 % (FAST) / +20 % (STRICT) when every matrix takes the same
 // path, but -27 % when the two matrices of a warp leave phase 1 at different columns and the
@@ -77,6 +119,9 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
         return launch_wsm<A, 8, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 16)
         return launch_wsm<A, 16, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
+    if (!S && x == nullptr && n > 16 && n <= 32 && wip_enabled())
+        return n <= 24 ? launch_wip<A, 3>(n, batch, a, l, e, p, k, sms, st)
+                       : launch_wip<A, 4>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 32)
         return wsm_pack_pref() ? launch_wsm<A, 16, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
                                : launch_wsm<A, 32, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
