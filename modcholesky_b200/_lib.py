@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmodchol_b200.so")
+# MODCHOL_LIB: another in-tree build of the same sources (kernel-tuning experiments, tools/)
+LIB_PATH = os.environ.get("MODCHOL_LIB") or os.path.join(_HERE, "csrc", "libmodchol_b200.so")
 
 GMW81, SE90, SE99 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -59,13 +59,20 @@ def _env():
     return env
 
 
-def build_library(force: bool = False, verbose: bool = False, jobs: int | None = None) -> str:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, jobs: int | None = None,
+                  variant: str | None = None, extra: list[str] | None = None) -> str:
+    """variant: build into csrc/build_<variant>/ and libmodchol_b200.<variant>.so with the extra
+    nvcc flags (kernel-tuning experiments; selected at run time with MODCHOL_LIB)."""
+    global OBJ, LIB
+    if variant:
+        OBJ = os.path.join(CSRC, "build_" + variant)
+        LIB = os.path.join(CSRC, f"libmodchol_b200.{variant}.so")
+    elif not force and not is_stale():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     exe, env = nvcc(), _env()
 
-    extra = os.environ.get("MODCHOL_NVCC_EXTRA", "").split()   # experiments, e.g. -DMODCHOL_MINB32=5
+    extra = (extra or []) + os.environ.get("MODCHOL_NVCC_EXTRA", "").split()   # e.g. -DMODCHOL_WIP_MINB=5
 
     def compile_one(unit):
         src, obj, defs = unit
@@ -88,5 +95,7 @@ def build_library(force: bool = False, verbose: bool = False, jobs: int | None =
 
 if __name__ == "__main__":
     import sys
-    build_library(force=True, verbose="-v" in sys.argv)
-    print(LIB)
+    args = [a for a in sys.argv[1:] if a != "-v"]
+    # python -m modcholesky_b200.build [-v] [variant -Dflag ...]
+    print(build_library(force=True, verbose="-v" in sys.argv, variant=args[0] if args else None,
+                        extra=args[1:]))

@@ -1,52 +1,66 @@
-// wip_kernels.cuh -- FAST-mode GMW81 / SE90 / SE99 for 8 < n <= 32 with IMPLICIT pivoting:
+// wip_kernels.cuh -- FAST-mode GMW81 / SE90 / SE99 for 16 < n <= 32 with IMPLICIT pivoting:
 // one warp per matrix, lane i owns ORIGINAL row i for the whole factorisation and nothing is
-// ever swapped (gmw81.rs:39-134, se90.rs:38-181, se99.rs:35-201; swap of utils.rs:30-49 is
+// ever swapped (gmw81.rs:39-134, se90.rs:38-181, se99.rs:35-201; the swap of utils.rs:30-49 is
 // replaced by the per-lane `pos`, the permuted position the reference would hold the row at).
 //
-//   * storage: packed lower triangle in shared memory in ORIGINAL coordinates, element
-//     (i,k), i >= k, at T(i)+k.  The slot of (i, r) is dead as soon as row/column r has been
-//     the pivot, so the factor is stored in place: after step t with pivot row r the slot
-//     (max(i,r), min(i,r)) holds L(i,t) for every row i still alive and (r,r) holds L(r,t).
-//   * a step reads the pivot column straight from those slots: lane i > r reads T(i)+r
-//     (the triangular numbers are a permutation modulo 16 on aligned runs of 16 rows), lane
-//     i < r reads T(r)+i (contiguous) -- one LDS per lane, no swap, no row scalars to exchange.
-//   * the trailing block is brought up to date every FOUR steps on the FP64 tensor pipe
-//     (mma.sync.m8n8k4.f64): the four new columns go through a 32x4 panel in shared memory
-//     whose layout makes both the per-step column write and the fragment load conflict free;
-//     between updates a column needs at most three fused multiply-adds per lane.  Tiles are
-//     fixed 8x8 blocks of the original index space; a store is predicated on "row and column
-//     both still alive" so that finished slots keep their L entries.
+// Where the data lives (per warp):
+//   * C, the symmetric trailing matrix in ORIGINAL coordinates, lives in REGISTERS as the
+//     accumulator fragments of ten fixed 8x8 tiles (lower block triangle, 40 registers per
+//     lane) and is brought up to date every FOUR steps by one mma.sync.m8n8k4.f64 (DMMA) per
+//     tile -- no load or store of C around the tensor-pipe instruction.  After each update the
+//     fragments are also DUMPED into a packed lower triangle in shared memory (element (i,k),
+//     i >= k, at T(i)+k), which is all a step needs: lane i > r reads T(i)+r (the triangular
+//     numbers are a permutation modulo 16 on aligned runs of 16 rows), lane i < r reads T(r)+i
+//     (contiguous) -- one LDS per lane and step, no swap, no row scalars to exchange.  Between
+//     updates a column needs at most three fused multiply-adds with the pending panel columns.
+//   * the four pending columns go through a 32x4 panel in shared memory whose layout makes the
+//     per-step column write and the fragment load both conflict free.
+//   * L is written to TENSOR MEMORY: lane i stores L(i,t) at step t into its own TMEM lane,
+//     columns 2t..2t+1 (tcgen05.st, one instruction per step, off the shared-memory pipe), so
+//     finished entries never have to be protected from the dumps.  In the epilogue every lane
+//     reads its row back (tcgen05.ld), zeroes the entries beyond its final position and writes
+//     it to row pos of the output with 256-bit stores -- no un-permutation pass.
 //   * pivot search: order-preserving integer keys + ONE REDUX when the high word of the
 //     maximum is unique (practically always); ties fall back to the full first-in-position
 //     search of utils.rs:52-91 on (hi, lo, pos).
 //   * the Gershgorin bounds of a phase 2 that starts at column 0 (symmetric-uniform inputs)
-//     come from the absolute column sums accumulated while the matrix is loaded.
+//     come from absolute column sums accumulated while the matrix streams in.
 // FAST arithmetic only (fused multiply-add, rsqrt scaling, tree-ordered norms): results agree
 // with the oracle within the north-star tolerances, not bit for bit -- STRICT mode keeps the
 // position-ordered kernels of wsm_se.cuh / wsm_gmw.cuh.
 #pragma once
 #include "wsm_se.cuh"
 
+#ifndef MODCHOL_WIP_DMMA_SUM
+#define MODCHOL_WIP_DMMA_SUM 1   /* column norm: two DMMAs (1) or five shuffle rounds (0) */
+#endif
+
 namespace modchol {
 
 constexpr int kWipTri = 528;       // T(32) doubles of packed triangle
 constexpr int kWipPanelLd = 36;    // panel column stride: == 4 (mod 16) doubles, see above
-constexpr int kWipDoubles = kWipTri + 4 * kWipPanelLd + 16;   // + inverse permutation (32 ints)
+#ifndef MODCHOL_WIP_KB
+#define MODCHOL_WIP_KB 8
+#endif
+constexpr int kWipKB = MODCHOL_WIP_KB;   // steps between two trailing updates (4 or 8)
+constexpr int kWipDoubles = kWipTri + kWipKB * kWipPanelLd;
+constexpr int kWipWarps = 4;       // warp w of a block owns TMEM lanes [32 w, 32 w + 32)
+constexpr int kWipTmemCols = 64;   // 32 doubles of L per lane
 
-using IC0 = std::integral_constant<int, 0>;
-using IC1 = std::integral_constant<int, 1>;
-using IC2 = std::integral_constant<int, 2>;
-using IC3 = std::integral_constant<int, 3>;
+template <int I>
+using IC = std::integral_constant<int, I>;
 
-__device__ __forceinline__ void sts_u32(unsigned a, unsigned v)
+// f(IC<I>) for I = Begin .. End-1 until one call returns true (-> true)
+template <int Begin, int End, typename F>
+__device__ __forceinline__ bool wip_steps(F&& f)
 {
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned lds_u32(unsigned a)
-{
-    unsigned v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
+    if constexpr (Begin < End) {
+        if (f(IC<Begin>{}))
+            return true;
+        return wip_steps<Begin + 1, End>(static_cast<F&&>(f));
+    } else {
+        return false;
+    }
 }
 
 // order-preserving key without the -0 fold of make_key (FAST: +-0 ties are rounding ties)
@@ -65,190 +79,351 @@ __device__ __forceinline__ int wip_pivot_lane(int khi, unsigned klo, bool cand, 
 {
     const int mh = __reduce_max_sync(kFull, cand ? khi : (int)0x80000000);
     const bool c1 = cand && khi == mh;
-    const unsigned b1 = __ballot_sync(kFull, c1);
-    if (__popc(b1) == 1)
-        return __ffs(b1) - 1;
-    const unsigned ml = __reduce_max_sync(kFull, c1 ? klo : 0u);
-    const bool win = c1 && klo == ml;
-    unsigned mpos = __reduce_min_sync(kFull, win ? (unsigned)pos : 1024u);
-    if (mpos > 255u)
-        mpos = (unsigned)j;
-    return __ffs(__ballot_sync(kFull, !fin && pos == (int)mpos)) - 1;
-}
-
-// Trailing update with the cnt (<= 4) columns of the panel:
-//     C(i,k) -= sum_c P(i,c) P(k,c)      for every pair of rows i >= k that are both alive,
-// one DMMA per 8x8 tile of the original index space.  Fragments: lane l holds
-// A[l/4][l%4] = P(8 bi + l/4, l%4), the same pattern serves as B for block column bj, and
-// C[l/4][2 (l%4) + {0,1}].  fmask = finished rows (bit i), including the rows >= n.
-template <int NB>
-__device__ __noinline__ void wip_rank_update(unsigned wb, unsigned pnb, unsigned fmask, int cnt, int lane)
-{
-    const int r8 = lane >> 2, c4 = lane & 3;
-    double frag[NB];
-    const unsigned pf = pnb + 8u * (unsigned)(kWipPanelLd * c4 + r8);
-#pragma unroll
-    for (int b = 0; b < NB; ++b)
-        frag[b] = lds_f64_or_zero(c4 < cnt, pf + 64u * b);
-    const unsigned rowdead = fmask >> r8;          // bit 8 bi     : row 8 bi + r8 is finished
-    const unsigned coldead = fmask >> (2 * c4);    // bit 8 bj + e : column 8 bj + 2 c4 + e
-    const unsigned r0 = wb + 8u * (unsigned)(tri(r8) + 2 * c4);
-#pragma unroll
-    for (int bi = 0; bi < NB; ++bi) {
-        if (((fmask >> (8 * bi)) & 0xffu) == 0xffu)
-            continue;
-        // T(8 bi + r8) = T(8 bi) + T(r8) + 8 bi r8
-        const unsigned ra = r0 + 8u * (unsigned)(tri(8 * bi) + 8 * bi * r8);
-        const bool rl = ((rowdead >> (8 * bi)) & 1u) == 0u;
-        const double na = -frag[bi];
-#pragma unroll
-        for (int bj = 0; bj <= bi; ++bj) {
-            if (((fmask >> (8 * bj)) & 0xffu) == 0xffu)
-                continue;
-            bool p0 = rl && ((coldead >> (8 * bj)) & 1u) == 0u;
-            bool p1 = rl && ((coldead >> (8 * bj + 1)) & 1u) == 0u;
-            if (bi == bj) {
-                p0 = p0 && 2 * c4 <= r8;
-                p1 = p1 && 2 * c4 + 1 <= r8;
-            }
-            const unsigned a = ra + 64u * bj;
-            const double c0 = lds_f64(a), c1 = lds_f64(a + 8);
-            double d0, d1;
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
-                         : "=d"(d0), "=d"(d1) : "d"(na), "d"(frag[bj]), "d"(c0), "d"(c1));
-            sts_f64_if(p0, a, d0);
-            sts_f64_if(p1, a + 8, d1);
-        }
+    unsigned b1 = __ballot_sync(kFull, c1);
+    if (__popc(b1) != 1) {
+        const unsigned ml = __reduce_max_sync(kFull, c1 ? klo : 0u);
+        const bool win = c1 && klo == ml;
+        unsigned mpos = __reduce_min_sync(kFull, win ? (unsigned)pos : 1024u);
+        if (mpos > 255u)
+            mpos = (unsigned)j;
+        b1 = __ballot_sync(kFull, !fin && pos == (int)mpos);
     }
+    return 31 - __clz(b1);   // exactly one bit is set
 }
 
-template <int kAlgo, int NB, int kWarps, int kMinBlocks>
-__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
-wip_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
+__device__ __forceinline__ double wip_neg(double x)   // -x on the integer pipe
+{
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
+// sum of x over the 32 lanes on the FP64 tensor pipe, returned to every lane: with x as the B
+// fragment (lane l holds B[l%4][l/4]) and A = 1, D[m][n] = sum_k x_{4n+k} is the sum of lane
+// quad n, and lane l receives D[l/4][2(l%4)], D[l/4][2(l%4)+1] -- the four lanes of a quad end
+// up holding all eight quad sums between them; their pairwise sums as the A fragment of a second
+// DMMA against B = 1 give the total in every lane.  Three instructions instead of five shuffle
+// rounds (15), and a shorter dependency chain.
+__device__ __forceinline__ double wip_sum32(double x)
+{
+    double q0, q1, s0, s1;
+    const double one = 1.0, zero = 0.0;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %4};"
+                 : "=d"(q0), "=d"(q1) : "d"(one), "d"(x), "d"(zero));
+    const double h = dadd(q0, q1);
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %4};"
+                 : "=d"(s0), "=d"(s1) : "d"(h), "d"(one), "d"(zero));
+    return s0;
+}
+
+// pivots outside the safe range of the rsqrt formulas (<= 0, NaN, Inf, subnormal, huge): the
+// STRICT formulas (rare; the fast values are computed unconditionally and overridden here)
+__device__ __forceinline__ void wip_slow_p2(double piv, double normj, double col, double& sq, double& t, double& cs)
+{
+    sq = dsqrt(piv);
+    t = dsub(1.0, ddiv(normj, piv));
+    cs = ddiv(col, sq);
+}
+__device__ __forceinline__ void wip_slow_p1(double piv, double col, double dg, double& sq, double& cs, double& dgn,
+                                         double& nv)
+{
+    sq = dsqrt(piv);
+    cs = ddiv(col, sq);
+    dgn = __fma_rn(-cs, cs, dg);
+    nv = dsub(dg, ddiv(dmul(col, col), piv));
+}
+__device__ __forceinline__ void wip_slow_gmw(double dj, double& sq, double& y)
+{
+    sq = dsqrt(dj);
+    y = ddiv(1.0, sq);
+}
+
+// L(lane, t) -> this lane's TMEM row (taddr: warp-uniform, lane quarter + column 2 t)
+__device__ __forceinline__ void wip_tmem_store(unsigned taddr, double v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                 :: "r"(taddr), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+
+// eight doubles of this lane's TMEM row, starting at column taddr
+__device__ __forceinline__ void wip_tmem_load8(unsigned taddr, double (&v)[8])
+{
+    unsigned w[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]),
+                   "=r"(w[7]), "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]),
+                   "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        v[u] = __hiloint2double((int)w[2 * u + 1], (int)w[2 * u]);
+}
+
+__device__ __forceinline__ void stg_v4f64(double* p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// kN: compile-time n (0: run-time n <= 8 NB).  kRegC: C fragments resident in registers (40 per
+// lane, 20 warps per SM) or in the shared-memory triangle only (one LDS/DMMA/STS round trip per
+// tile and update, 64 registers, 32 warps per SM).
+template <int kAlgo, int NB, int kN, bool kRegC, int kMinBlocks>
+__global__ void __launch_bounds__(kWipWarps * 32, kMinBlocks)
+wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __restrict__ L,
            double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
 {
     extern __shared__ double sm[];
+    __shared__ unsigned tmem_base;
+    constexpr int kTiles = NB * (NB + 1) / 2;
+    const int n = kN ? kN : n_rt;
     int lane = threadIdx.x & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(lane));   // pinned (see wsm_se.cuh)
-    const int wib = threadIdx.x >> 5;
+    // warp index through a shuffle from lane 0: ptxas then treats it (and the batch loop below) as
+    // warp-uniform, so the .sync operations inside need no divergence check (BRA.DIV)
+    const int wib = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+
+    // ---- tensor memory: 64 columns per block, warp w owns lanes [32 w, 32 w + 32) -------------
+    if (wib == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(&tmem_base)), "n"(kWipTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tw = tmem_base + ((unsigned)(wib * 32) << 16);
+
     unsigned wb = (unsigned)__cvta_generic_to_shared(sm + (size_t)wib * kWipDoubles);
     asm volatile("mov.u32 %0, %0;" : "+r"(wb));
-    const unsigned pnb = wb + 8u * kWipTri;                  // 4 panel columns of kWipPanelLd
-    const unsigned invb = pnb + 8u * 4 * kWipPanelLd;        // inverse permutation, 32 ints
+    const unsigned pnb = wb + 8u * kWipTri;                  // kWipKB panel columns of kWipPanelLd
     unsigned tib = wb + 8u * (unsigned)tri(lane);            // byte address of slot (lane, 0)
     asm volatile("mov.u32 %0, %0;" : "+r"(tib));
     const unsigned pcol = pnb + 8u * (unsigned)lane;         // this lane's entry of panel column 0
+    const int r8 = lane >> 2, c4 = lane & 3;
+    const unsigned pf = pnb + 8u * (unsigned)(kWipPanelLd * c4 + r8);      // fragment source
+    const unsigned fr0 = wb + 8u * (unsigned)(tri(r8) + 2 * c4);           // slot (r8, 2 c4)
+    const bool pd0 = 2 * c4 <= r8, pd1 = 2 * c4 + 1 <= r8;                 // diagonal tiles: lower part
     const size_t nn = (size_t)n * n;
-    const long long nslots = (long long)gridDim.x * kWarps;
+    const long long nslots = (long long)gridDim.x * kWipWarps;
     const bool has = lane < n;
+    // 128/256-bit global accesses need aligned bases and an even row length
+    const bool wide = kN != 0 && kN % 8 == 0 && (((size_t)A | (size_t)L) & 31) == 0;
 
-    for (long long b = (long long)blockIdx.x * kWarps + wib; b < batch; b += nslots) {
-        // ---- load: row i of A by the whole warp (lane = column), lower part into the packed
-        // triangle; this lane's diagonal element and absolute off-diagonal column sum (== row
-        // sum: A symmetric) on the fly -------------------------------------------------------
-        const double* src = A + (size_t)b * nn + lane;
-        unsigned dst = wb + 8u * (unsigned)lane;
-        double dg = 0.0, asum = 0.0;
-        unsigned long long omax = 0ull;   // GMW81: max |a_ik|, i != k, as an integer (gmw81.rs:52-58)
-        __syncwarp();
-        auto take = [&](int i, double v) {
-            sts_f64_if(lane <= i, dst, v);
-            dst += 8u * (unsigned)(i + 1);
-            if (lane == i) {
-                dg = v;
-            } else if (kAlgo == kGMW81) {
-                const unsigned long long a = (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
-                omax = a > omax ? a : omax;   // |.| of non-NaN doubles order like their bits
-            } else {
-                asum = dadd(asum, fabs(v));
+    for (long long b = (long long)blockIdx.x * kWipWarps + wib; b < batch; b += nslots) {
+        const double* Ab = A + (size_t)b * nn;
+        // ---- load -----------------------------------------------------------------------------
+        // kRegC: the ten tiles straight into the accumulator fragments (lane l: rows 8 bi + l/4,
+        // columns 8 bj + 2 (l%4) + {0,1}); otherwise row by row into the packed triangle (lane =
+        // column).  SE: absolute off-diagonal column sum (== row sum, A is symmetric) from the
+        // streamed rows; GMW81: off-diagonal maximum (gmw81.rs:52-58), kept as integers (|.| of
+        // non-NaN doubles order like their bits).
+        double cf[kRegC ? kTiles : 1][2];
+        if constexpr (kRegC) {
+            const double* fp = Ab + (size_t)r8 * n + 2 * c4;
+#pragma unroll
+            for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                for (int bj = 0; bj <= bi; ++bj) {
+                    const int t = bi * (bi + 1) / 2 + bj;
+                    const double* p = fp + (size_t)(8 * bi) * n + 8 * bj;
+                    if (wide) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+                        cf[t][0] = v.x;
+                        cf[t][1] = v.y;
+                    } else {
+                        const int i = 8 * bi + r8, k = 8 * bj + 2 * c4;
+                        cf[t][0] = (i < n && k < n) ? __ldg(p) : 0.0;
+                        cf[t][1] = (i < n && k + 1 < n) ? __ldg(p + 1) : 0.0;
+                    }
+                }
+        }
+        double dg = has ? __ldg(Ab + (size_t)lane * (n + 1)) : 0.0;   // this lane's diagonal element
+        double asum = 0.0;
+        unsigned long long om = 0ull;
+        if constexpr (!kRegC)
+            __syncwarp();   // the previous matrix's readers of the triangle are done
+        if constexpr (kAlgo != kGMW81 || !kRegC) {
+            const double* src = Ab + lane;
+            unsigned dst = wb + 8u * (unsigned)lane;
+            auto take = [&](int i, double v) {
+                if constexpr (!kRegC) {
+                    sts_f64_if(lane <= i, dst, v);
+                    dst += 8u * (unsigned)(i + 1);
+                }
+                if constexpr (kAlgo == kGMW81) {
+                    const unsigned long long a =
+                        (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
+                    om = (lane != i && a > om) ? a : om;
+                } else {
+                    asum = dadd(asum, fabs(v));
+                }
+            };
+            int i = 0;
+            for (; i + 8 <= n; i += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = has ? __ldg(src + (size_t)u * n) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    take(i + u, v[u]);
+                src += (size_t)8 * n;
             }
+            for (; i < n; ++i) {
+                take(i, has ? __ldg(src) : 0.0);
+                src += n;
+            }
+            asum = dsub(asum, fabs(dg));
+        }
+
+        // fragments -> packed triangle in shared memory (every slot, finished or not: L lives in
+        // tensor memory, so the triangle only ever holds C as of the last update)
+        auto dump = [&]() {
+            if constexpr (!kRegC)
+                return;
+#pragma unroll
+            for (int bi = 0; bi < NB; ++bi) {
+                // T(8 bi + r8) = T(8 bi) + T(r8) + 8 bi r8
+                const unsigned ra = fr0 + 8u * (unsigned)(tri(8 * bi) + 8 * bi * r8);
+#pragma unroll
+                for (int bj = 0; bj <= bi; ++bj) {
+                    const int t = bi * (bi + 1) / 2 + bj;
+                    if (bi == bj) {
+                        sts_f64_if(pd0, ra + 64u * bj, cf[t][0]);
+                        sts_f64_if(pd1, ra + 64u * bj + 8, cf[t][1]);
+                    } else {
+                        sts_f64(ra + 64u * bj, cf[t][0]);
+                        sts_f64(ra + 64u * bj + 8, cf[t][1]);
+                    }
+                }
+            }
+            __syncwarp();
         };
-        int i = 0;
-        for (; i + 8 <= n; i += 8) {
-            double v[8];
+        // C(i,k) -= sum_{c < cnt} P(i,c) P(k,c): one DMMA per tile (A fragment of block row bi:
+        // lane l holds P(8 bi + l/4, l%4); the same pattern is the B fragment of block column bj)
+        auto rank_update = [&](int cnt) {
+            constexpr int KC = kWipKB / 4;   // k-chunks of four panel columns
+            double frag[KC][NB], nfrag[KC][NB];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                v[u] = has ? __ldg(src + (size_t)u * n) : 0.0;
+            for (int h = 0; h < KC; ++h)
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                take(i + u, v[u]);
-            src += (size_t)8 * n;
+                for (int q = 0; q < NB; ++q) {
+                    const unsigned a = pf + 8u * (unsigned)(4 * kWipPanelLd * h) + 64u * q;
+                    frag[h][q] = cnt == kWipKB ? lds_f64(a) : lds_f64_or_zero(4 * h + c4 < cnt, a);
+                    nfrag[h][q] = wip_neg(frag[h][q]);
+                }
+#pragma unroll
+            for (int bi = 0; bi < NB; ++bi) {
+                const unsigned ra = fr0 + 8u * (unsigned)(tri(8 * bi) + 8 * bi * r8);
+#pragma unroll
+                for (int bj = 0; bj <= bi; ++bj) {
+                    if constexpr (kRegC) {
+                        const int t = bi * (bi + 1) / 2 + bj;
+#pragma unroll
+                        for (int h = 0; h < KC; ++h)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                         : "+d"(cf[t][0]), "+d"(cf[t][1]) : "d"(nfrag[h][bi]), "d"(frag[h][bj]));
+                    } else {
+                        // (diagonal tiles: the entries above the diagonal are other rows' slots --
+                        // loaded, updated and not stored)
+                        double c0 = lds_f64(ra + 64u * bj), c1 = lds_f64(ra + 64u * bj + 8);
+#pragma unroll
+                        for (int h = 0; h < KC; ++h)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                         : "+d"(c0), "+d"(c1) : "d"(nfrag[h][bi]), "d"(frag[h][bj]));
+                        if (bi == bj) {
+                            sts_f64_if(pd0, ra + 64u * bj, c0);
+                            sts_f64_if(pd1, ra + 64u * bj + 8, c1);
+                        } else {
+                            sts_f64(ra + 64u * bj, c0);
+                            sts_f64(ra + 64u * bj + 8, c1);
+                        }
+                    }
+                }
+            }
+            if constexpr (kRegC)
+                dump();
+            else
+                __syncwarp();
+        };
+        if constexpr (kRegC) {
+            __syncwarp();   // the previous matrix's readers of the triangle are done
+            dump();
+        } else {
+            __syncwarp();
         }
-        for (; i < n; ++i) {
-            take(i, has ? __ldg(src) : 0.0);
-            src += n;
-        }
-        __syncwarp();
 
         double ev = 0.0;
         int pos = lane;                       // permuted position of this lane's row
         bool fin = !has;                      // row already eliminated (or no row)
         unsigned fmask = n >= 32 ? 0u : (0xffffffffu << n);
         int j = 0, cnt = 0, kstart = -1;
-        double csr[3] = {0.0, 0.0, 0.0};      // this row's entries of the pending panel columns
+        double csr[kWipKB - 1];               // this row's entries of the pending panel columns
+#pragma unroll
+        for (int c = 0; c < kWipKB - 1; ++c)
+            csr[c] = 0.0;
         bool win;
 
         // current value of C(lane, r): stored slot minus the C pending panel columns
-        auto column = [&](auto ctag, int r, unsigned& addr) -> double {
+        auto column = [&](auto ctag, int r) -> double {
             constexpr int C = decltype(ctag)::value;
-            const unsigned tr = wb + 8u * (unsigned)tri(r);
-            addr = lane > r ? tib + 8u * (unsigned)r : tr + 8u * (unsigned)lane;
-            double col = lds_f64(addr);
+            const unsigned tr = wb + 4u * (unsigned)(r * (r + 1));
+            double col = lds_f64(lane > r ? tib + 8u * (unsigned)r : tr + 8u * (unsigned)lane);
 #pragma unroll
             for (int c = 0; c < C; ++c)
                 col = __fma_rn(-csr[c], lds_f64(pnb + 8u * (unsigned)(kWipPanelLd * c + r)), col);
             return col;
         };
-        auto column_rt = [&](int c, int r, unsigned& addr) -> double {
-            switch (c) {
-            case 0: return column(IC0{}, r, addr);
-            case 1: return column(IC1{}, r, addr);
-            case 2: return column(IC2{}, r, addr);
-            default: return column(IC3{}, r, addr);
-            }
-        };
-        // s = sqrt(pivot), y with cs = col * y, 1 / pivot (FAST formulas inside the safe range)
-        auto scale = [&](double piv, double& sq, double& y, double& inv_piv) -> bool {
-            const bool fast = fast_range_ok(piv);
-            if (fast) {
-                y = rsqrt_normal(piv);
-                sq = dmul(piv, y);
-                inv_piv = dmul(y, y);
-            } else {
-                sq = dsqrt(piv);
-                y = 0.0;
-                inv_piv = 0.0;
-            }
-            return fast;
+        auto column_rt = [&](int c, int r) -> double {
+            double v = 0.0;
+            wip_steps<0, kWipKB>([&](auto ctag) {
+                if (c != decltype(ctag)::value)
+                    return false;
+                v = column(ctag, r);
+                return true;
+            });
+            return v;
         };
         // the pivot row r takes position j; the row that sat there takes r's old position
         auto take_position = [&](int r) {
             const int pr = __shfl_sync(kFull, pos, r);
-            if (pos == j)
-                pos = pr;
-            if (lane == r)
-                pos = j;
+            pos = pos == j ? pr : pos;
+            pos = lane == r ? j : pos;
         };
-        // column j of L: cs into the dead slots of column r and into panel column C, sq on the
-        // diagonal; row r is finished
-        auto retire = [&](auto ctag, int r, unsigned addr, double cs, double sq) {
+        // column j of L: cs (sq for the pivot row) into tensor memory and panel column C;
+        // row r is finished
+        auto retire = [&](auto ctag, int r, double cs, double sq) {
             constexpr int C = decltype(ctag)::value;
-            sts_f64_if(!fin, addr, lane == r ? sq : cs);
+            wip_tmem_store(tw + 2u * (unsigned)j, lane == r ? sq : cs);
             sts_f64(pcol + 8u * (unsigned)(kWipPanelLd * C), cs);
-            if constexpr (C < 3)
+            if constexpr (C < kWipKB - 1)
                 csr[C] = cs;
-            if (lane == r)
-                fin = true;
+            fin = fin || lane == r;
             fmask |= 1u << r;
             __syncwarp();
             ++j;
         };
 
         if constexpr (kAlgo == kGMW81) {
-            // ---- GMW81, symmetric form (see wsm_gmw.cuh): slots hold c_is / sqrt(d_s) ---------
+            // ---- GMW81, symmetric form (see wsm_gmw.cuh): L entries are c_is / sqrt(d_s) ------
+            // off-diagonal maximum (gmw81.rs:52-58) from the fragments, as integers (|.| of
+            // non-NaN doubles order like their bits); diagonal-tile entries with row == column
+            // are skipped
+            if constexpr (kRegC)
+#pragma unroll
+            for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                for (int bj = 0; bj <= bi; ++bj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned long long a =
+                            (unsigned long long)__double_as_longlong(cf[bi * (bi + 1) / 2 + bj][e]) & 0x7fffffffffffffffull;
+                        const bool diag = bi == bj && 2 * c4 + e == r8;
+                        om = (!diag && a > om) ? a : om;
+                    }
             const double diag_max = warp_extreme<true>(kFull, fabs(dg), has, 0.0, win);
-            const unsigned ohi = __reduce_max_sync(kFull, (unsigned)(omax >> 32));
-            const unsigned olo = __reduce_max_sync(kFull, (unsigned)(omax >> 32) == ohi ? (unsigned)omax : 0u);
+            const unsigned ohi = __reduce_max_sync(kFull, (unsigned)(om >> 32));
+            const unsigned olo = __reduce_max_sync(kFull, (unsigned)(om >> 32) == ohi ? (unsigned)om : 0u);
             const double off_max = __hiloint2double((int)ohi, (int)olo);
             const double nf = (double)n;
             const double delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(diag_max, off_max)));
@@ -261,40 +436,29 @@ wip_kernel(int n, long long batch, const double* __restrict__ A, double* __restr
                 const unsigned klo = (unsigned)__double2loint(dg);
                 const int r = wip_pivot_lane(khi, klo, !fin && dg == dg, fin, pos, j);
                 take_position(r);
-                unsigned addr;
-                const double col = column(ctag, r, addr);   // lane r: c_jj from the same updates
+                const double col = column(ctag, r);   // lane r: c_jj from the same updates
                 const double cjj = __shfl_sync(kFull, col, r);
                 const bool live = !fin && lane != r;
                 // theta = max_{i>j} |c_ij| (gmw81.rs:87-100), d_j (gmw81.rs:102)
                 const double theta = warp_extreme<true>(kFull, fabs(col), live, 0.0, win);
                 const double tb = dmul(theta, rbeta);
                 const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);
-                double sq, y;
-                if (fast_range_ok(dj)) {
-                    y = rsqrt_normal(dj);
-                    sq = dmul(dj, y);
-                } else {
-                    sq = dsqrt(dj);
-                    y = ddiv(1.0, sq);
-                }
+                double y = rsqrt_normal(dj);
+                double sq = dmul(dj, y);
+                if (!fast_range_ok(dj))
+                    wip_slow_gmw(dj, sq, y);
                 const double cs = dmul(col, y);
-                if (live)
-                    dg = __fma_rn(-cs, cs, dg);                 // gmw81.rs:104-109
-                if (lane == r)
-                    ev = dsub(dj, cjj);                         // gmw81.rs:110
-                retire(ctag, r, addr, cs, sq);
+                dg = live ? __fma_rn(-cs, cs, dg) : dg;             // gmw81.rs:104-109
+                ev = lane == r ? dsub(dj, cjj) : ev;                // gmw81.rs:110
+                retire(ctag, r, cs, sq);
             };
             while (j < n) {
-                gmw_step(IC0{});
-                if (j == n) break;
-                gmw_step(IC1{});
-                if (j == n) break;
-                gmw_step(IC2{});
-                if (j == n) break;
-                gmw_step(IC3{});
-                if (j == n) break;
-                wip_rank_update<NB>(wb, pnb, fmask, 4, lane);
-                __syncwarp();
+                if (wip_steps<0, kWipKB>([&](auto ctag) {
+                        gmw_step(ctag);
+                        return j == n;
+                    }))
+                    break;
+                rank_update(kWipKB);
             }
         } else {
             double g = dsub(dg, asum);            // Gershgorin bound if phase 2 starts at column 0
@@ -324,15 +488,17 @@ wip_kernel(int n, long long batch, const double* __restrict__ A, double* __restr
                     }
                 }
                 take_position(r);
-                unsigned addr;
-                const double col = column(ctag, r, addr);
+                const double col = column(ctag, r);
                 const bool live = !fin && lane != r;
-                double sq, y, inv_piv;
-                const bool fast = scale(piv, sq, y, inv_piv);
-                const double cs = fast ? dmul(col, y) : ddiv(col, sq);
-                const double dgn = __fma_rn(-cs, cs, dg);
+                const bool fast = fast_range_ok(piv);
+                const double y = rsqrt_normal(piv);
+                double sq = dmul(piv, y);
+                double cs = dmul(col, y);
+                double dgn = __fma_rn(-cs, cs, dg);
                 // look-ahead value (se90.rs:70-77, se99.rs:82-89); FAST: the updated diagonal
-                const double nv = fast ? dgn : dsub(dg, ddiv(dmul(col, col), piv));
+                double nv = dgn;
+                if (!fast)
+                    wip_slow_p1(piv, col, dg, sq, cs, dgn, nv);
                 const double la = warp_extreme<false>(kFull, nv, live, INFINITY, win);
                 have_dmin = fast;
                 dmin_carry = la;
@@ -341,42 +507,35 @@ wip_kernel(int n, long long batch, const double* __restrict__ A, double* __restr
                     kstart = j;
                     return 1;
                 }
-                if (live)
-                    dg = dgn;
-                retire(ctag, r, addr, cs, sq);
+                dg = live ? dgn : dg;
+                retire(ctag, r, cs, sq);
                 return j == n ? 2 : 0;
             };
-            int st;
+            int st = 0;
             for (;;) {
-                cnt = 0;
-                if ((st = p1_step(IC0{})) != 0) break;
-                cnt = 1;
-                if ((st = p1_step(IC1{})) != 0) break;
-                cnt = 2;
-                if ((st = p1_step(IC2{})) != 0) break;
-                cnt = 3;
-                if ((st = p1_step(IC3{})) != 0) break;
-                wip_rank_update<NB>(wb, pnb, fmask, 4, lane);
-                __syncwarp();
+                if (wip_steps<0, kWipKB>([&](auto ctag) {
+                        cnt = decltype(ctag)::value;   // pending panel columns at this step
+                        st = p1_step(ctag);
+                        return st != 0;
+                    }))
+                    break;
+                rank_update(kWipKB);
             }
 
             // ---- phase 2 -------------------------------------------------------------------
             if (st == 1 && kAlgo == kSE99 && kstart == n - 1) {   // se99.rs:115-119
-                const int u = __ffs(__ballot_sync(kFull, !fin)) - 1;
+                const int u = 31 - __clz(__ballot_sync(kFull, !fin));
                 const double ljj = __shfl_sync(kFull, dg, u);
                 const double ej = tail1x1_e(ljj, gamma);
-                if (lane == u) {
-                    ev = ej;
-                    sts_f64(tib + 8u * (unsigned)lane, dsqrt(dadd(ljj, ej)));
-                }
+                ev = lane == u ? ej : ev;
+                wip_tmem_store(tw + 2u * (unsigned)(n - 1), dsqrt(dadd(ljj, ej)));
             } else if (st == 1) {
                 if (j > 0) {
                     // the Gershgorin bounds need the trailing block as the reference holds it: apply
                     // the pending columns, then g_i = a_ii - sum_{k alive, k != i} |a_ik|
                     // (se90.rs:105-110, se99.rs:125-130)
                     if (cnt > 0) {
-                        wip_rank_update<NB>(wb, pnb, fmask, cnt, lane);
-                        __syncwarp();
+                        rank_update(cnt);
                         cnt = 0;
                     }
                     double s = 0.0;
@@ -397,55 +556,44 @@ wip_kernel(int n, long long batch, const double* __restrict__ A, double* __restr
                     const int r = wip_pivot_lane(khi, klo, !fin && g == g, fin, pos, j);
                     take_position(r);
                     double piv = __shfl_sync(kFull, dg, r);
-                    unsigned addr;
-                    const double col = column(ctag, r, addr);
+                    const double col = column(ctag, r);
                     const bool live = !fin && lane != r;
                     const double acol = live ? abs_bits(col) : 0.0;
                     // E_jj (se90.rs:124-131, se99.rs:144-151)
-                    const double normj = warp_sum_tree<32>(kFull, acol);
+                    const double normj = MODCHOL_WIP_DMMA_SUM ? wip_sum32(acol) : warp_sum_tree<32>(kFull, acol);
                     const double ej = max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
                     piv = dadd(piv, ej);
                     delta_prev = ej;
-                    double sq, y, inv_piv;
-                    const bool fast = scale(piv, sq, y, inv_piv);
-                    // bound update (se90.rs:134-139, se99.rs:154-159)
+                    // bound update (se90.rs:134-139, se99.rs:154-159) and column scaling
                     const bool upd = fabs(dsub(piv, normj)) > MODCHOL_EPS;
-                    double t = 0.0;
-                    if (upd)
-                        t = fast ? __fma_rn(-normj, inv_piv, 1.0) : dsub(1.0, ddiv(normj, piv));
-                    const double cs = fast ? dmul(col, y) : ddiv(col, sq);
-                    if (live) {
-                        dg = __fma_rn(-cs, cs, dg);
-                        if (upd)
-                            g = __fma_rn(acol, t, g);
-                    }
-                    if (lane == r)
-                        ev = ej;
-                    retire(ctag, r, addr, cs, sq);
+                    const double y = rsqrt_normal(piv);
+                    double sq = dmul(piv, y);
+                    double t = __fma_rn(-normj, dmul(y, y), 1.0);
+                    double cs = dmul(col, y);
+                    if (!fast_range_ok(piv))
+                        wip_slow_p2(piv, normj, col, sq, t, cs);
+                    dg = live ? __fma_rn(-cs, cs, dg) : dg;
+                    g = (live && upd) ? __fma_rn(acol, t, g) : g;
+                    ev = lane == r ? ej : ev;
+                    retire(ctag, r, cs, sq);
                 };
                 while (j + 2 < n) {
-                    p2_step(IC0{});
-                    cnt = 1;
-                    if (j + 2 >= n) break;
-                    p2_step(IC1{});
-                    cnt = 2;
-                    if (j + 2 >= n) break;
-                    p2_step(IC2{});
-                    cnt = 3;
-                    if (j + 2 >= n) break;
-                    p2_step(IC3{});
+                    if (wip_steps<0, kWipKB>([&](auto ctag) {
+                            p2_step(ctag);
+                            cnt = decltype(ctag)::value + 1;
+                            return cnt < kWipKB && j + 2 >= n;
+                        }))
+                        break;
                     cnt = 0;
-                    wip_rank_update<NB>(wb, pnb, fmask, 4, lane);
-                    __syncwarp();
+                    rank_update(kWipKB);
                 }
                 // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186): the two rows
                 // alive sit at positions n-2 and n-1
-                const int u0 = __ffs(__ballot_sync(kFull, !fin && pos == n - 2)) - 1;
-                const int u1 = __ffs(__ballot_sync(kFull, !fin && pos == n - 1)) - 1;
+                const int u0 = 31 - __clz(__ballot_sync(kFull, !fin && pos == n - 2));
+                const int u1 = 31 - __clz(__ballot_sync(kFull, !fin && pos == n - 1));
                 double a00 = __shfl_sync(kFull, dg, u0);
                 double a11 = __shfl_sync(kFull, dg, u1);
-                unsigned addr;
-                const double c2 = column_rt(cnt, u0, addr);
+                const double c2 = column_rt(cnt, u0);
                 double a10 = __shfl_sync(kFull, c2, u1);
                 double lhi, llo;
                 eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);   // lower storage: m[0,1] == m[1,0]
@@ -457,47 +605,52 @@ wip_kernel(int n, long long batch, const double* __restrict__ A, double* __restr
                 a00 = dsqrt(a00);
                 a10 = ddiv(a10, a00);
                 a11 = dsqrt(dsub(a11, dmul(a10, a10)));
-                if (lane == u0) {
-                    ev = en;
-                    sts_f64(tib + 8u * (unsigned)lane, a00);
-                }
-                if (lane == u1) {
-                    ev = en;
-                    sts_f64(addr, a10);
-                    sts_f64(tib + 8u * (unsigned)lane, a11);
-                }
+                ev = (lane == u0 || lane == u1) ? en : ev;
+                wip_tmem_store(tw + 2u * (unsigned)(n - 2), lane == u0 ? a00 : a10);
+                wip_tmem_store(tw + 2u * (unsigned)(n - 1), a11);
             }
         }
 
-        // ---- epilogue: L row q = the slots of row inv[q] in pivot order (strict upper
-        // explicitly zero, se99.rs:189-192), e in original order (se99.rs:194-198), p ---------
-        if (has)
-            sts_u32(invb + 4u * (unsigned)pos, (unsigned)lane);
-        __syncwarp();
-        const int ct = has ? (int)lds_u32(invb + 4u * (unsigned)lane) : 0;   // row at position `lane`
-        const unsigned tct = wb + 8u * (unsigned)tri(ct);
+        // ---- epilogue: this lane's row of L leaves tensor memory for row `pos` of the output,
+        // zero beyond the diagonal (se99.rs:189-192); e in original order (se99.rs:194-198); p ---
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         if (L) {
-            double* dstp = L + (size_t)b * nn + lane;
-#pragma unroll 4
-            for (int q = 0; q < n; ++q) {
-                const int iq = __shfl_sync(kFull, ct, q);
-                const unsigned tq = __shfl_sync(kFull, tct, q);
-                const unsigned a = iq > ct ? tq + 8u * (unsigned)ct : tct + 8u * (unsigned)iq;
-                const double v = lds_f64_or_zero(lane <= q, a);
-                if (has)
-                    *dstp = v;
-                dstp += n;
+            double* dstp = L + (size_t)b * nn + (size_t)pos * n;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (8 * c >= n)
+                    break;
+                double v[8];
+                wip_tmem_load8(tw + 16u * c, v);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = 8 * c + u <= pos ? v[u] : 0.0;
+                if (wide && has) {
+                    stg_v4f64(dstp + 8 * c, v[0], v[1], v[2], v[3]);
+                    stg_v4f64(dstp + 8 * c + 4, v[4], v[5], v[6], v[7]);
+                } else if (!wide && has) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (8 * c + u < n)
+                            dstp[8 * c + u] = v[u];
+                }
             }
         }
         if (has) {
             if (E)
                 E[(size_t)b * n + lane] = ev;
             if (P)
-                P[(size_t)b * n + lane] = (unsigned long long)ct;
+                P[(size_t)b * n + pos] = (unsigned long long)lane;
         }
         if (K && lane == 0)
             K[b] = kstart;
     }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wib == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     :: "r"(tmem_base), "n"(kWipTmemCols) : "memory");
 }
 
 }  // namespace modchol

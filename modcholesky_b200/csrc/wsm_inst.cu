@@ -1,5 +1,6 @@
 // wsm_inst.cu -- instantiates the shared-memory-resident warp kernels (wsm_se.cuh) for ONE
 // (algorithm, mode) pair: -DMODCHOL_INST_ALGO={1,2} -DMODCHOL_INST_STRICT={0,1}.
+#include <cstdio>
 #include <cstdlib>
 
 #include "warp_kernels.cuh"
@@ -56,16 +57,18 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
 
 // FAST mode, 16 < n <= 32, no fused solve: the implicit-pivoting kernels (wip_kernels.cuh).
 // The launch attributes and the occupancy are queried once per instantiation and device.
-#ifndef MODCHOL_WIP_MINB
-#define MODCHOL_WIP_MINB 8
+#ifndef MODCHOL_WIP_REGC
+#define MODCHOL_WIP_REGC 0   /* C fragments in registers (1) or in the shared-memory triangle (0) */
 #endif
-template <int kAlgo, int NB>
+#ifndef MODCHOL_WIP_MINB
+#define MODCHOL_WIP_MINB (MODCHOL_WIP_REGC ? 5 : 8)
+#endif
+template <int kAlgo, int NB, int kN>
 static cudaError_t launch_wip(int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
-    constexpr int kWarps = 4;
-    auto kern = wip_kernel<kAlgo, NB, kWarps, MODCHOL_WIP_MINB>;
-    constexpr size_t smem = (size_t)kWarps * kWipDoubles * sizeof(double);
+    auto kern = wip_kernel<kAlgo, NB, kN, MODCHOL_WIP_REGC != 0, MODCHOL_WIP_MINB>;
+    constexpr size_t smem = (size_t)kWipWarps * kWipDoubles * sizeof(double);
     static int occ_dev[64];   // resident blocks per SM, 0 = not yet queried on that device
     int dev = 0;
     cudaError_t ce = cudaGetDevice(&dev);
@@ -77,15 +80,29 @@ static cudaError_t launch_wip(int n, long long batch, const double* a, double* l
         ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxShared);
         if (ce != cudaSuccess) return ce;
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWipWarps * 32, smem);
         if (ce != cudaSuccess) return ce;
+        if (getenv("MODCHOL_DEBUG"))
+            fprintf(stderr, "[modchol] wip kernel algo %d NB %d N %d: occupancy query -> %d blocks/SM, smem %zu\n",
+                    kAlgo, NB, kN, occ, smem);
+        // the occupancy query answers 1 for any kernel that allocates tensor memory (it assumes
+        // all 512 columns); this kernel takes kWipTmemCols per block, so the real limit is the
+        // register file / shared memory one, capped by 512 / kWipTmemCols
+        cudaFuncAttributes fa;
+        ce = cudaFuncGetAttributes(&fa, kern);
+        if (ce != cudaSuccess) return ce;
+        int by_regs = 65536 / (fa.numRegs * kWipWarps * 32);
+        int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+        occ = by_regs < by_smem ? by_regs : by_smem;
+        if (const char* f = getenv("MODCHOL_WIP_OCC")) occ = atoi(f);
         if (occ < 1) occ = 1;
+        if (occ > 512 / kWipTmemCols) occ = 512 / kWipTmemCols;   // tensor memory: 512 columns per SM
         if (dev < 64) occ_dev[dev] = occ;   // benign race: every writer stores the same value
     }
-    long long blocks = (batch + kWarps - 1) / kWarps;
+    long long blocks = (batch + kWipWarps - 1) / kWipWarps;
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
-    kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
     return cudaGetLastError();
 }
 
@@ -113,6 +130,9 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
 {
     constexpr int A = MODCHOL_INST_ALGO;
     constexpr bool S = MODCHOL_INST_STRICT != 0;
+    if (!S && x == nullptr && n > 12 && n <= 16 && wip_enabled())
+        return n < 16 ? launch_wip<A, 2, 0>(n, batch, a, l, e, p, k, sms, st)
+                      : launch_wip<A, 2, 16>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 4)
         return launch_wsm<A, 4, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 8)
@@ -120,8 +140,9 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
     if (n <= 16)
         return launch_wsm<A, 16, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (!S && x == nullptr && n > 16 && n <= 32 && wip_enabled())
-        return n <= 24 ? launch_wip<A, 3>(n, batch, a, l, e, p, k, sms, st)
-                       : launch_wip<A, 4>(n, batch, a, l, e, p, k, sms, st);
+        return n <= 24 ? launch_wip<A, 3, 0>(n, batch, a, l, e, p, k, sms, st)
+               : n < 32 ? launch_wip<A, 4, 0>(n, batch, a, l, e, p, k, sms, st)
+                        : launch_wip<A, 4, 32>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 32)
         return wsm_pack_pref() ? launch_wsm<A, 16, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
                                : launch_wsm<A, 32, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);

@@ -29,7 +29,7 @@ def bench_style(rng, b, n):
         q = np.eye(n)
         for _ in range(3):
             w = rng.uniform(-1, 1, size=(n, 1))
-            q = q @ (np.eye(n) - 2.0 / float(w.T @ w) * (w @ w.T))
+            q = q @ (np.eye(n) - 2.0 / (w.T @ w).item() * (w @ w.T))
         d = rng.uniform(-1, 1000, size=n)
         d[rng.integers(n)] = rng.uniform(-1, 0)
         a = q @ np.diag(d) @ q.T

@@ -294,8 +294,15 @@ def test_fused_factor_solve(oracle, torch_cuda, n):
                 x2 = m.solve_batched(d, rd).cpu().numpy()
                 x, df = m.factor_solve_batched(algo, ad, rd, mode=mode, return_factors=True)
                 x = x.cpu().numpy()
-                # the factors that come with it are the plain call's, bit for bit
-                assert torch.equal(df.l, d.l) and torch.equal(df.e, d.e) and torch.equal(df.p, d.p)
+                if mode == "strict":
+                    # the factors that come with it are the plain call's, bit for bit
+                    assert torch.equal(df.l, d.l) and torch.equal(df.e, d.e) and torch.equal(df.p, d.p)
+                else:
+                    # FAST: the plain call may run the implicit-pivoting kernels (12 < n <= 32) while
+                    # the fused call keeps the position-ordered ones -- same pivots, roundings differ
+                    assert torch.equal(df.p, d.p)
+                    assert torch.allclose(df.l, d.l, rtol=1e-9, atol=1e-11)
+                    assert torch.allclose(df.e, d.e, rtol=1e-9, atol=1e-11)
                 assert torch.equal(df.phase2_start, d.phase2_start)
                 # x without asking for the factors (NULL outputs) is the same x
                 x0 = m.factor_solve_batched(algo, ad, rd, mode=mode).cpu().numpy()
