@@ -50,6 +50,28 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+def _dev_tensor(t, name: str, dtype, shape=None, device=None):
+    """A torch tensor about to cross the C-ABI as a DEVICE pointer: it must be a CUDA tensor of
+    exactly `dtype` (the kernels reinterpret the bytes), on `device` when given, of `shape`
+    when given (None entries are free).  Returns it contiguous."""
+    import torch
+    if not _is_torch(t):
+        raise TypeError(f"{name}: expected a torch CUDA tensor next to the other device buffers, "
+                        f"got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name}: torch tensors must live on a CUDA device (pass numpy for host "
+                         "data); modcholesky_b200 has no CPU path")
+    dtypes = dtype if isinstance(dtype, tuple) else (dtype,)
+    if t.dtype not in dtypes:
+        raise TypeError(f"{name}: expected {' or '.join(str(d) for d in dtypes)}, got {t.dtype}")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name}: lives on {t.device}, the other buffers on {device}")
+    if shape is not None:
+        if t.ndim != len(shape) or any(w is not None and int(g) != int(w) for g, w in zip(t.shape, shape)):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
 def _factor_numpy(algo: int, mode: int, a: np.ndarray, ngpus: int = 0) -> Decomposition:
     a = np.ascontiguousarray(a, dtype=np.float64)
     b, n = a.shape[0], a.shape[1]
@@ -72,12 +94,7 @@ def _factor_numpy(algo: int, mode: int, a: np.ndarray, ngpus: int = 0) -> Decomp
 
 def _factor_torch(algo: int, mode: int, a) -> Decomposition:
     import torch
-    if not a.is_cuda:
-        raise ValueError("torch tensors must live on a CUDA device (pass numpy for host data); "
-                         "modcholesky_b200 has no CPU path")
-    if a.dtype != torch.float64:
-        raise TypeError("expected float64")
-    a = a.contiguous()
+    a = _dev_tensor(a, "a", torch.float64)
     b, n = a.shape[0], a.shape[1]
     with torch.cuda.device(a.device):
         l = torch.empty_like(a)
@@ -137,7 +154,7 @@ def gershgorin_circles_batched(a):
     b, n = a.shape[0], a.shape[1]
     if _is_torch(a):
         import torch
-        a = a.contiguous()
+        a = _dev_tensor(a, "a", torch.float64)
         with torch.cuda.device(a.device):
             out = torch.empty((b, n, 2), dtype=torch.float64, device=a.device)
             st = torch.cuda.current_stream(a.device).cuda_stream
@@ -159,13 +176,16 @@ def verify_batched(a, d: Decomposition):
     b, n = a.shape[0], a.shape[1]
     if _is_torch(a):
         import torch
+        a = _dev_tensor(a, "a", torch.float64, (b, n, n))
+        dl = _dev_tensor(d.l, "d.l", torch.float64, (b, n, n), a.device)
+        de = _dev_tensor(d.e, "d.e", torch.float64, (b, n), a.device)
+        dp = _dev_tensor(d.p, "d.p", (torch.int64, torch.uint64), (b, n), a.device)
         with torch.cuda.device(a.device):
             resid = torch.empty((b,), dtype=torch.float64, device=a.device)
             flags = torch.empty((b,), dtype=torch.int32, device=a.device)
             st = torch.cuda.current_stream(a.device).cuda_stream
             rc = L.modchol_verify_batched_f64(
-                b, n, a.contiguous().data_ptr(), d.l.contiguous().data_ptr(),
-                d.e.contiguous().data_ptr(), d.p.contiguous().data_ptr(), resid.data_ptr(),
+                b, n, a.data_ptr(), dl.data_ptr(), de.data_ptr(), dp.data_ptr(), resid.data_ptr(),
                 flags.data_ptr(), _lib.MEM_DEVICE, ctypes.c_void_p(st))
         _lib.check(rc)
         return resid, flags
@@ -191,18 +211,22 @@ def solve_batched(d: Decomposition, b):
     bt, nrhs, n = b.shape
     if _is_torch(b):
         import torch
-        b = b.contiguous()
+        b = _dev_tensor(b, "b", torch.float64)
+        dl = _dev_tensor(d.l, "d.l", torch.float64, (bt, n, n), b.device)
+        dp = _dev_tensor(d.p, "d.p", (torch.int64, torch.uint64), (bt, n), b.device)
         with torch.cuda.device(b.device):
             x = torch.empty_like(b)
             st = torch.cuda.current_stream(b.device).cuda_stream
-            rc = L.modchol_solve_batched_f64(bt, n, nrhs, d.l.contiguous().data_ptr(),
-                                             d.p.contiguous().data_ptr(), b.data_ptr(), x.data_ptr(),
-                                             _lib.MEM_DEVICE, ctypes.c_void_p(st))
+            rc = L.modchol_solve_batched_f64(bt, n, nrhs, dl.data_ptr(), dp.data_ptr(), b.data_ptr(),
+                                             x.data_ptr(), _lib.MEM_DEVICE, ctypes.c_void_p(st))
         _lib.check(rc)
     else:
         b = np.ascontiguousarray(b, dtype=np.float64)
         l = np.ascontiguousarray(d.l, dtype=np.float64)
         p = np.ascontiguousarray(d.p, dtype=np.uint64)
+        if l.shape != (bt, n, n) or p.shape != (bt, n):
+            raise ValueError(f"b of shape {tuple(b.shape)} does not match the factors "
+                             f"{tuple(l.shape)}, {tuple(p.shape)}")
         x = np.empty_like(b)
         _lib.check(L.modchol_solve_batched_f64(bt, n, nrhs, l.ctypes.data, p.ctypes.data,
                                                b.ctypes.data, x.ctypes.data, _lib.MEM_HOST, None))
@@ -226,7 +250,8 @@ def factor_solve_batched(algo, a, b, mode="strict", return_factors: bool = False
     d = None
     if _is_torch(a):
         import torch
-        a, b = a.contiguous(), b.contiguous()
+        a = _dev_tensor(a, "a", torch.float64)
+        b = _dev_tensor(b, "b", torch.float64, (bt, nrhs, n), a.device)
         with torch.cuda.device(a.device):
             x = torch.empty_like(b)
             ptrs = [None, None, None, None]

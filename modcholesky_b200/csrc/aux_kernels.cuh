@@ -113,8 +113,7 @@ verify_kernel(long long batch, int n, const double* __restrict__ A, const double
 // The working vector lives in shared memory (n doubles per warp).
 __global__ void __launch_bounds__(128)
 solve_kernel(long long batch, int n, int nrhs, const double* __restrict__ L,
-             const unsigned long long* __restrict__ P, const double* __restrict__ B,
-             double* __restrict__ X)
+             const unsigned long long* __restrict__ P, const double* B, double* X)   // X may alias B
 {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;

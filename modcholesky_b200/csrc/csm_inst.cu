@@ -1,5 +1,6 @@
 // csm_inst.cu -- instantiates the block-per-matrix packed shared-memory kernels (csm_se.cuh) for
 // ONE (algorithm, mode) pair: -DMODCHOL_INST_ALGO={1,2} -DMODCHOL_INST_STRICT={0,1}.
+#include "launch_cache.cuh"
 #include "warp_kernels.cuh"
 #include "csm_gmw.cuh"
 #include "csm_se.cuh"
@@ -21,15 +22,9 @@ static cudaError_t launch_csm(int n, long long batch, const double* a, double* l
             return csm_se_kernel<kAlgo, kStrict, kThreads, kMinBlocks, false, kDmma && !kStrict>;
     }();
     const size_t smem = csm_smem_bytes(n, 0, kDmma && !kStrict);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return ce;
-    ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              (int)cudaSharedmemCarveoutMaxShared);
-    if (ce != cudaSuccess) return ce;
     int occ = 1;
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
+    cudaError_t ce = cached_occupancy(kern, kThreads, smem, (size_t)227 * 1024, &occ);
     if (ce != cudaSuccess) return ce;
-    if (occ < 1) occ = 1;
     long long blocks = batch;
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every block strides over the batch
@@ -60,10 +55,8 @@ static cudaError_t launch_csm_spill(int n, long long batch, const double* a, dou
         ++S;
     const size_t smem = csm_smem_bytes(n, S, kPanel);
     if (smem > (size_t)optin) return cudaErrorInvalidValue;
-    ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return ce;
-    ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              (int)cudaSharedmemCarveoutMaxShared);
+    int occ_unused = 1;
+    ce = cached_occupancy(kern, kThreads, smem, (size_t)optin, &occ_unused);
     if (ce != cudaSuccess) return ce;
     long long blocks = batch < sms ? batch : sms;   // one block per SM, persistent
     double* spill = nullptr;

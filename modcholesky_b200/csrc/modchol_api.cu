@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -53,10 +54,17 @@ struct Slot {
     unsigned long long* p = nullptr;
     int* k = nullptr;
     size_t cap_a = 0, cap_v = 0, cap_k = 0;  // capacities in elements: a/l, e/p, k
+    // pinned bounce buffers for callers whose memory is pageable (numpy, ndarray): allocated on
+    // first use, same capacities as the device buffers
+    double *ha = nullptr, *hl = nullptr, *he = nullptr;
+    unsigned long long* hp = nullptr;
+    int* hk = nullptr;
+    size_t hcap_a = 0, hcap_v = 0, hcap_k = 0;
 };
 struct DeviceCtx {
     std::mutex mu;  // serialises host-pointer calls on this device
-    bool init = false;
+    std::once_flag once;   // guards the three attribute fields below
+    int init_rc = 0;       // cudaError_t of the attribute queries
     int sms = 0;
     int smem_optin = 0;
     Slot slots[kSlots];
@@ -74,14 +82,25 @@ int device_count()
     return n;
 }
 
+// Device attributes, queried once per device; safe to call from any thread (DEVICE-mode calls
+// never take the device mutex).
 int ctx_init(int dev)
 {
     DeviceCtx& c = g_ctx[dev];
-    if (c.init)
-        return MODCHOL_OK;
-    CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    c.init = true;
+    std::call_once(c.once, [&c, dev]() {
+        cudaError_t e = cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+            e = cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        // the batched solve keeps 4 n doubles per block in dynamic shared memory: 64 KB at
+        // n = MODCHOL_MAX_N, above the 48 KB default
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(4 * MODCHOL_MAX_N * sizeof(double)));
+        c.init_rc = (int)e;
+    });
+    if (c.init_rc != 0)
+        return fail(MODCHOL_ERR_CUDA, "device %d attribute query failed: %s", dev,
+                    cudaGetErrorString((cudaError_t)c.init_rc));
     return MODCHOL_OK;
 }
 
@@ -96,6 +115,70 @@ void slot_free(Slot& s)
     s.p = nullptr;
     s.k = nullptr;
     s.cap_a = s.cap_v = s.cap_k = 0;
+}
+
+void slot_free_host(Slot& s)
+{
+    if (s.ha) cudaFreeHost(s.ha);
+    if (s.hl) cudaFreeHost(s.hl);
+    if (s.he) cudaFreeHost(s.he);
+    if (s.hp) cudaFreeHost(s.hp);
+    if (s.hk) cudaFreeHost(s.hk);
+    s.ha = s.hl = s.he = nullptr;
+    s.hp = nullptr;
+    s.hk = nullptr;
+    s.hcap_a = s.hcap_v = s.hcap_k = 0;
+}
+
+int slot_reserve_host(Slot& s, size_t mats, int n)
+{
+    const size_t need_a = mats * (size_t)n * n, need_v = mats * (size_t)n, need_k = mats;
+    if (s.ha && need_a <= s.hcap_a && need_v <= s.hcap_v && need_k <= s.hcap_k)
+        return MODCHOL_OK;
+    const size_t ca = std::max(need_a, s.hcap_a), cv = std::max(need_v, s.hcap_v),
+                 ck = std::max(need_k, s.hcap_k);
+    slot_free_host(s);
+    CUDA_TRY(cudaHostAlloc(&s.ha, ca * sizeof(double), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s.hl, ca * sizeof(double), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s.he, cv * sizeof(double), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s.hp, cv * sizeof(unsigned long long), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&s.hk, ck * sizeof(int), cudaHostAllocDefault));
+    s.hcap_a = ca;
+    s.hcap_v = cv;
+    s.hcap_k = ck;
+    return MODCHOL_OK;
+}
+
+// true when the DMA engines can read/write this host range directly (cudaHostAlloc,
+// cudaHostRegister or managed memory); pageable memory goes through the pinned bounce buffers
+bool host_ptr_is_pinned(const void* ptr)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// memcpy on a few host threads (one core moves ~10 GB/s; the PCIe link wants ~50)
+void parallel_memcpy(void* dst, const void* src, size_t bytes)
+{
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned want = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, hw / 2)), bytes >> 22);
+    if (want <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / want) + 4095) & ~(size_t)4095;
+    for (unsigned t = 0; t < want; ++t) {
+        const size_t lo = std::min(bytes, (size_t)t * per), hi = std::min(bytes, lo + per);
+        if (hi > lo)
+            th.emplace_back([=]() { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    for (auto& t : th)
+        t.join();
 }
 
 int slot_reserve(Slot& s, size_t mats, int n)
@@ -228,7 +311,11 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
 }
 
 // host pointers: stage the batch through the device in chunks on kSlots streams so that
-// H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1 overlap.
+// H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1 overlap.  Pinned caller memory is
+// read and written by the DMA engines directly; pageable caller memory (numpy, ndarray) goes
+// through cached pinned bounce buffers, copied by a few host threads while the other slots'
+// transfers run -- a cudaMemcpyAsync on pageable memory would block the host until the chunk's
+// kernel is done and serialise the pipeline.
 int factor_host_on_device(int dev, int algo, int mode, long long batch, int n, const double* a,
                           double* l, double* e, unsigned long long* p, int* k)
 {
@@ -247,35 +334,84 @@ int factor_host_on_device(int dev, int algo, int mode, long long batch, int n, c
     chunk = std::min(chunk, (batch + kSlots - 1) / kSlots);
     chunk = std::max<long long>(chunk, 1);
     const int nslots = (int)std::min<long long>(kSlots, (batch + chunk - 1) / chunk);
+    const bool bounce_in = !host_ptr_is_pinned(a);
+    const bool bounce_out = !(host_ptr_is_pinned(l) && host_ptr_is_pinned(e) && host_ptr_is_pinned(p) &&
+                              (!k || host_ptr_is_pinned(k)));
     for (int s = 0; s < nslots; ++s) {
         rc = slot_reserve(c.slots[s], (size_t)chunk, n);
+        if (rc == MODCHOL_OK && (bounce_in || bounce_out))
+            rc = slot_reserve_host(c.slots[s], (size_t)chunk, n);
         if (rc)
             return rc;
     }
+    struct Pending { long long off = 0, cnt = 0; };
+    Pending pend[kSlots];
+    // results of the chunk a slot last worked on: wait for its stream, then (pageable caller) copy
+    // them out of the bounce buffers
+    auto retire = [&](int si) -> cudaError_t {
+        Slot& s = c.slots[si];
+        const cudaError_t ce = cudaStreamSynchronize(s.stream);
+        const Pending pd = pend[si];
+        pend[si] = Pending();
+        if (ce != cudaSuccess || pd.cnt == 0 || !bounce_out)
+            return ce;
+        parallel_memcpy(l + (size_t)pd.off * nn, s.hl, (size_t)pd.cnt * nn * sizeof(double));
+        memcpy(e + (size_t)pd.off * n, s.he, (size_t)pd.cnt * n * sizeof(double));
+        memcpy(p + (size_t)pd.off * n, s.hp, (size_t)pd.cnt * n * sizeof(unsigned long long));
+        if (k)
+            memcpy(k + pd.off, s.hk, (size_t)pd.cnt * sizeof(int));
+        return cudaSuccess;
+    };
+    cudaError_t ce = cudaSuccess;
+    rc = MODCHOL_OK;
     long long off = 0;
-    int ci = 0;
-    while (off < batch) {
+    for (int ci = 0; off < batch && ce == cudaSuccess && rc == MODCHOL_OK; ++ci) {
         const long long cnt = std::min(chunk, batch - off);
-        Slot& s = c.slots[ci % nslots];
-        CUDA_TRY(cudaMemcpyAsync(s.a, a + (size_t)off * nn, (size_t)cnt * nn * sizeof(double),
-                                 cudaMemcpyHostToDevice, s.stream));
+        const int si = ci % nslots;
+        Slot& s = c.slots[si];
+        if (pend[si].cnt && (bounce_in || bounce_out))
+            ce = retire(si);   // the slot's bounce buffers are about to be reused
+        if (ce != cudaSuccess)
+            break;
+        const double* src = a + (size_t)off * nn;
+        if (bounce_in) {
+            parallel_memcpy(s.ha, src, (size_t)cnt * nn * sizeof(double));
+            src = s.ha;
+        }
+        ce = cudaMemcpyAsync(s.a, src, (size_t)cnt * nn * sizeof(double), cudaMemcpyHostToDevice, s.stream);
+        if (ce != cudaSuccess)
+            break;
         rc = factor_device(dev, algo, mode, cnt, n, s.a, s.l, s.e, s.p, k ? s.k : nullptr, s.stream);
         if (rc)
-            return rc;
-        CUDA_TRY(cudaMemcpyAsync(l + (size_t)off * nn, s.l, (size_t)cnt * nn * sizeof(double),
-                                 cudaMemcpyDeviceToHost, s.stream));
-        CUDA_TRY(cudaMemcpyAsync(e + (size_t)off * n, s.e, (size_t)cnt * n * sizeof(double),
-                                 cudaMemcpyDeviceToHost, s.stream));
-        CUDA_TRY(cudaMemcpyAsync(p + (size_t)off * n, s.p, (size_t)cnt * n * sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, s.stream));
-        if (k)
-            CUDA_TRY(cudaMemcpyAsync(k + off, s.k, (size_t)cnt * sizeof(int),
-                                     cudaMemcpyDeviceToHost, s.stream));
+            break;
+        double* dl = bounce_out ? s.hl : l + (size_t)off * nn;
+        double* de = bounce_out ? s.he : e + (size_t)off * n;
+        unsigned long long* dp = bounce_out ? s.hp : p + (size_t)off * n;
+        int* dk = bounce_out ? s.hk : (k ? k + off : nullptr);
+        ce = cudaMemcpyAsync(dl, s.l, (size_t)cnt * nn * sizeof(double), cudaMemcpyDeviceToHost, s.stream);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(de, s.e, (size_t)cnt * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(dp, s.p, (size_t)cnt * n * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, s.stream);
+        if (ce == cudaSuccess && k)
+            ce = cudaMemcpyAsync(dk, s.k, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+        pend[si].off = off;
+        pend[si].cnt = cnt;
         off += cnt;
-        ++ci;
     }
-    for (int s = 0; s < nslots; ++s)
-        CUDA_TRY(cudaStreamSynchronize(c.slots[s].stream));
+    // drain -- on the error paths too: no copy may still be writing the caller's buffers when
+    // this function returns
+    for (int si = 0; si < nslots; ++si) {
+        if (ce == cudaSuccess && rc == MODCHOL_OK)
+            ce = retire(si);
+        else
+            cudaStreamSynchronize(c.slots[si].stream);
+    }
+    if (rc)
+        return rc;
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "host staging pipeline: %s", cudaGetErrorString(ce));
     return MODCHOL_OK;
 }
 
@@ -398,6 +534,7 @@ void modchol_shutdown(void)
             if (s.stream) {
                 cudaStreamSynchronize(s.stream);
                 slot_free(s);
+                slot_free_host(s);
                 cudaStreamDestroy(s.stream);
                 s.stream = nullptr;
             }

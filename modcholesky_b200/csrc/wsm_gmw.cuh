@@ -70,7 +70,7 @@ template <int G, int R, bool kStrict, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 wsm_gmw_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
                double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
-               int* __restrict__ K, const double* __restrict__ Bm, double* __restrict__ X, int nrhs)
+               int* __restrict__ K, const double* Bm, double* X, int nrhs)   // X may alias Bm
 {
     extern __shared__ double sm[];
     constexpr int kPack = 32 / G;   // matrices per warp, G lanes each (see wsm_se.cuh)

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "launch_cache.cuh"
 #include "warp_kernels.cuh"
 #include "wip_kernels.cuh"
 #include "wsm_gmw.cuh"
@@ -38,16 +39,12 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
     }();
     const int wstride = wsm_warp_doubles(n);
     const size_t smem = (size_t)kWarps * kPack * wstride * sizeof(double);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return ce;
-    // the matrices live in shared memory: ask for the largest shared-memory carve-out
-    ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              (int)cudaSharedmemCarveoutMaxShared);
-    if (ce != cudaSuccess) return ce;
+    // the matrices live in shared memory: largest carve-out; attributes and occupancy are cached
+    constexpr int kNmax = G * R;   // largest n this instantiation serves
+    const size_t smem_max = (size_t)kWarps * kPack * wsm_warp_doubles(kNmax) * sizeof(double);
     int occ = 1;
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem);
+    cudaError_t ce = cached_occupancy(kern, kWarps * 32, smem, smem_max, &occ);
     if (ce != cudaSuccess) return ce;
-    if (occ < 1) occ = 1;
     long long blocks = (batch + kWarps * kPack - 1) / (kWarps * kPack);
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every lane group strides over the batch
@@ -69,34 +66,26 @@ static cudaError_t launch_wip(int n, long long batch, const double* a, double* l
 {
     auto kern = wip_kernel<kAlgo, NB, kN, MODCHOL_WIP_REGC != 0, MODCHOL_WIP_MINB>;
     constexpr size_t smem = (size_t)kWipWarps * kWipDoubles * sizeof(double);
-    static int occ_dev[64];   // resident blocks per SM, 0 = not yet queried on that device
+    // The occupancy query answers 1 for any kernel that allocates tensor memory (it assumes all
+    // 512 columns); this kernel takes kWipTmemCols per block, so the real limit is the register
+    // file / shared memory one, capped by 512 / kWipTmemCols.  Computed once per device.
+    static int occ_dev[64];   // resident blocks per SM, 0 = not yet computed on that device
     int dev = 0;
     cudaError_t ce = cudaGetDevice(&dev);
     if (ce != cudaSuccess) return ce;
     int occ = dev < 64 ? occ_dev[dev] : 0;
     if (occ == 0) {
-        ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int ignored = 0;
+        ce = cached_occupancy(kern, kWipWarps * 32, smem, smem, &ignored);   // sets the attributes
         if (ce != cudaSuccess) return ce;
-        ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  (int)cudaSharedmemCarveoutMaxShared);
-        if (ce != cudaSuccess) return ce;
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWipWarps * 32, smem);
-        if (ce != cudaSuccess) return ce;
-        if (getenv("MODCHOL_DEBUG"))
-            fprintf(stderr, "[modchol] wip kernel algo %d NB %d N %d: occupancy query -> %d blocks/SM, smem %zu\n",
-                    kAlgo, NB, kN, occ, smem);
-        // the occupancy query answers 1 for any kernel that allocates tensor memory (it assumes
-        // all 512 columns); this kernel takes kWipTmemCols per block, so the real limit is the
-        // register file / shared memory one, capped by 512 / kWipTmemCols
         cudaFuncAttributes fa;
         ce = cudaFuncGetAttributes(&fa, kern);
         if (ce != cudaSuccess) return ce;
-        int by_regs = 65536 / (fa.numRegs * kWipWarps * 32);
-        int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+        const int by_regs = 65536 / (fa.numRegs * kWipWarps * 32);
+        const int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
         occ = by_regs < by_smem ? by_regs : by_smem;
-        if (const char* f = getenv("MODCHOL_WIP_OCC")) occ = atoi(f);
         if (occ < 1) occ = 1;
-        if (occ > 512 / kWipTmemCols) occ = 512 / kWipTmemCols;   // tensor memory: 512 columns per SM
+        if (occ > 512 / kWipTmemCols) occ = 512 / kWipTmemCols;
         if (dev < 64) occ_dev[dev] = occ;   // benign race: every writer stores the same value
     }
     long long blocks = (batch + kWipWarps - 1) / kWipWarps;

@@ -555,8 +555,7 @@ template <int G, int R>
 __device__ __forceinline__ void wsm_solve_in_place(unsigned mask, int n, unsigned wb,
                                                    const unsigned (&tib)[R], const int (&row)[R],
                                                    const bool (&rv)[R], const int (&perm)[R],
-                                                   const double* __restrict__ rhs,
-                                                   double* __restrict__ x, int nrhs)
+                                                   const double* rhs, double* x, int nrhs)
 {
     double rd[R];   // 1 / L_ii of this lane's positions
 #pragma unroll
@@ -605,7 +604,7 @@ template <int kAlgo, int G, int R, bool kStrict, int kWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 wsm_se_kernel(int n, int wstride, long long batch, const double* __restrict__ A,
               double* __restrict__ L, double* __restrict__ E, unsigned long long* __restrict__ P,
-              int* __restrict__ K, const double* __restrict__ Bm, double* __restrict__ X, int nrhs)
+              int* __restrict__ K, const double* Bm, double* X, int nrhs)   // X may alias Bm
 {
     extern __shared__ double sm[];
     // G lanes per matrix, 32 / G matrices per warp; every collective below is confined to the

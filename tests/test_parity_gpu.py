@@ -47,9 +47,17 @@ def _assert_bit_exact(tag, got, ref):
         f"{tag}: l differs, max abs {np.nanmax(np.abs(l - ref.l))}"
 
 
-def _assert_tolerance(tag, a, got, ref):
+RELAXED = {"checked": 0, "e_relaxed": 0, "recon_relaxed": 0}   # printed by the last test of this file
+
+
+def _assert_tolerance(tag, a, got, ref, algo=None):
+    """FAST-mode bars.  The plain north-star bars (E to 1e-10 of ||E||, reconstruction to 1e-12 of
+    ||A||) are asserted for every matrix except the two GMW81 situations in which they are below
+    the f64 resolution of the quantities themselves; those matrices are counted in RELAXED."""
     l, e, p, k = got
     b, n = a.shape[0], a.shape[1]
+    if algo is None:
+        algo = next((x for x in ALGOS if x in tag), "")
     ok = ~np.isnan(ref.l).any(axis=(1, 2))
     firm = ok & (ref.margin > TIE_MARGIN)
     same_p = (p == ref.p).all(axis=1)
@@ -58,12 +66,16 @@ def _assert_tolerance(tag, a, got, ref):
     cmp = firm & same_p
     escale = np.maximum(np.abs(ref.e).max(axis=1), 1e-300)
     anorm = np.maximum(np.abs(a).max(axis=(1, 2)), 1.0)
-    # E to 1e-10 relative to ||E||.  Where E is tiny (bench-style matrices: ||E|| ~ 1e-7 ||A||) every
-    # e_j = d_j - c_jj inherits the cancellation noise of c_jj = a_jj - sum(...), a few ulps of
-    # ||A|| in the reference itself, so agreement is required down to 1e-14 ||A|| (45 ulp), not below.
     de = np.abs(e - ref.e).max(axis=1)
-    bad = cmp & (de > TOL_E_REL * np.maximum(escale, 1e-4 * anorm))
-    assert not bad.any(), f"{tag}: E differs beyond 1e-10 rel in {bad.sum()} matrices"
+    # GMW81 only: e_j = d_j - c_jj inherits the cancellation noise of c_jj = a_jj - sum(...), a few
+    # ulps of ||A|| in the reference itself; where E is tiny (||E|| < 1e-4 ||A||, bench-style
+    # matrices) agreement is required down to 1e-14 ||A|| (45 ulp), not below.
+    e_bar = TOL_E_REL * escale
+    e_rel = (algo == "gmw81") & (escale < 1e-4 * anorm)
+    e_bar = np.where(e_rel, TOL_E_REL * 1e-4 * anorm, e_bar)
+    bad = cmp & (de > e_bar)
+    assert not bad.any(), f"{tag}: E differs beyond 1e-10 rel in {bad.sum()} matrices " \
+                          f"(worst {np.max(de[bad] / escale[bad]):.2e})"
     # reconstruction for EVERY finite matrix, tie or not
     llt = l @ np.transpose(l, (0, 2, 1))
     idx = p.astype(np.int64)
@@ -71,20 +83,29 @@ def _assert_tolerance(tag, a, got, ref):
     ep = np.take_along_axis(e, idx, 1)
     rhs = ap + np.einsum("bi,ij->bij", ep, np.eye(n))
     res = np.abs(llt - rhs).max(axis=(1, 2)) / anorm
-    # Where ||A + E|| >> ||A|| (GMW81 at n = 256 adds E ~ 1e3 ||A||) evaluating L L^T in f64 is
-    # itself off by more than 1e-12 ||A||: the bar is then the reference's own residual, computed
-    # the same way from the oracle's factors.
-    lr = ref.l
-    idr = ref.p.astype(np.int64)
-    apr = np.take_along_axis(np.take_along_axis(a, idr[:, :, None], 1), idr[:, None, :], 2)
-    rhr = apr + np.einsum("bi,ij->bij", np.take_along_axis(ref.e, idr, 1), np.eye(n))
-    with np.errstate(invalid="ignore"):
-        res_ref = np.abs(lr @ np.transpose(lr, (0, 2, 1)) - rhr).max(axis=(1, 2)) / anorm
-    # ... and never below a few ulps of the largest entry of A + E (the diagonal L L^T must hit)
-    ulps = 8.0 * np.finfo(np.float64).eps * np.nan_to_num(np.abs(rhr).max(axis=(1, 2))) / anorm
-    bar = np.maximum(np.maximum(TOL_RECON, 2.0 * np.nan_to_num(res_ref)), ulps)
-    assert (res[ok] <= bar[ok]).all(), f"{tag}: reconstruction {res[ok].max():.3e} > max(1e-12, 2x reference's, 8 ulp of |A+E|)"
+    # GMW81 only: where ||A + E|| > 1e3 ||A|| (n = 256 adds E ~ 1e3 ||A||) evaluating L L^T in f64
+    # is itself off by more than 1e-12 ||A||: the bar is then the reference's own residual, computed
+    # the same way from the oracle's factors, and never below a few ulps of the largest entry of
+    # A + E (which the diagonal of L L^T must hit).
+    aenorm = np.nan_to_num(np.abs(rhs).max(axis=(1, 2)))
+    r_rel = (algo == "gmw81") & (aenorm > 1e3 * anorm)
+    bar = np.full(b, TOL_RECON)
+    if r_rel.any():
+        lr = ref.l
+        idr = ref.p.astype(np.int64)
+        apr = np.take_along_axis(np.take_along_axis(a, idr[:, :, None], 1), idr[:, None, :], 2)
+        rhr = apr + np.einsum("bi,ij->bij", np.take_along_axis(ref.e, idr, 1), np.eye(n))
+        with np.errstate(invalid="ignore"):
+            res_ref = np.abs(lr @ np.transpose(lr, (0, 2, 1)) - rhr).max(axis=(1, 2)) / anorm
+        ulps = 8.0 * np.finfo(np.float64).eps * aenorm / anorm
+        relaxed = np.maximum(np.maximum(TOL_RECON, 2.0 * np.nan_to_num(res_ref)), ulps)
+        bar = np.where(r_rel, relaxed, bar)
+    assert (res[ok] <= bar[ok]).all(), \
+        f"{tag}: reconstruction {res[ok].max():.3e} exceeds the bar in {(res[ok] > bar[ok]).sum()} matrices"
     assert (np.triu(l, 1) == 0).all() and (e[ok] >= 0).all()
+    RELAXED["checked"] += int(ok.sum())
+    RELAXED["e_relaxed"] += int((cmp & e_rel).sum())
+    RELAXED["recon_relaxed"] += int((ok & r_rel).sum())
 
 
 # ---- the reference's own tests, run through the mirrored trait API on the GPU -------------
@@ -396,7 +417,7 @@ FULL = [
     ("se99", 16, 1 << 20, "uniform"),     # configs[1]
     ("se99", 32, 1 << 18, "uniform"),     # configs[4] per-GPU slice (2^20) is run by bench.py
     ("se90", 64, 200_000, "uniform"),     # configs[2]
-    ("gmw81", 256, 512, "uniform"),       # configs[3] (4096 in bench; 512 here for time)
+    ("gmw81", 256, 4096, "uniform"),      # configs[3]
 ]
 
 
@@ -433,3 +454,97 @@ def test_full_size_properties(oracle, torch_cuda, algo, n, batch, fam, mode):
     d2 = m.factor_batched(algo, a, mode=mode)
     torch.cuda.synchronize()
     assert torch.equal(d.l, d2.l) and torch.equal(d.e, d2.e) and torch.equal(d.p, d2.p)
+
+
+def test_multi_gpu_entry_point_two_devices(oracle, torch_cuda):
+    """modchol_factor_batched_multi_gpu_f64 on every visible device (runs where the box has >= 2
+    GPUs): contiguous slices, one host thread per device, results identical to one device."""
+    if m.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    a = matgen.make("wishart", 12, 30001, 32)        # odd batch: uneven slices
+    for mode in ("strict", "fast"):
+        d1 = m.factor_batched("se99", a, mode=mode, ngpus=-1)
+        d2 = m.factor_batched("se99", a, mode=mode, ngpus=2)
+        d0 = m.factor_batched("se99", a, mode=mode)
+        for d in (d1, d2):
+            assert np.array_equal(d.l, d0.l) and np.array_equal(d.e, d0.e) and np.array_equal(d.p, d0.p)
+            assert np.array_equal(d.phase2_start, d0.phase2_start)
+    ref = oracle.factor_batched("se99", a[:128])
+    d = m.factor_batched("se99", a, mode="strict", ngpus=-1)
+    assert np.array_equal(d.l[:128], ref.l) and np.array_equal(d.p[:128], ref.p)
+
+
+def test_pinned_and_pageable_host_buffers_agree(torch_cuda):
+    """HOST mem_kind: pinned caller memory is DMA'd directly, pageable memory goes through the
+    library's pinned bounce buffers; several chunks per slot so that buffers are reused."""
+    import ctypes
+    from modcholesky_b200 import _lib
+    torch = torch_cuda
+    n, b = 32, 60000        # 491 MB of input: 5+ chunks of 96 MB over three slots
+    a = matgen.make("uniform", 21, b, n)
+    dn = m.factor_batched("se99", a, mode="fast")                  # numpy: pageable
+    ah = torch.from_numpy(a).pin_memory()
+    lh = torch.empty((b, n, n), dtype=torch.float64).pin_memory()
+    eh = torch.empty((b, n), dtype=torch.float64).pin_memory()
+    ph = torch.empty((b, n), dtype=torch.int64).pin_memory()
+    kh = torch.empty((b,), dtype=torch.int32).pin_memory()
+    rc = _lib.lib().modchol_factor_batched_f64(_lib.SE99, _lib.MODE_FAST, b, n, ah.data_ptr(), lh.data_ptr(),
+                                               eh.data_ptr(), ph.data_ptr(), kh.data_ptr(), _lib.MEM_HOST, None)
+    _lib.check(rc)
+    assert np.array_equal(lh.numpy(), dn.l) and np.array_equal(eh.numpy(), dn.e)
+    assert np.array_equal(ph.numpy().astype(np.uint64), dn.p) and np.array_equal(kh.numpy(), dn.phase2_start)
+    dd = m.factor_batched("se99", torch.from_numpy(a).cuda(), mode="fast")
+    assert np.array_equal(dd.l.cpu().numpy(), dn.l)
+
+
+@pytest.mark.parametrize("n", [1537, 2048])
+def test_solve_at_the_largest_sizes(torch_cuda, n):
+    """The batched solve keeps 4 n doubles of dynamic shared memory per block: above n = 1536 that
+    is more than the 48 KB default and needs the opt-in attribute (MODCHOL_MAX_N = 2048)."""
+    rng = np.random.default_rng(n)
+    b = 2
+    w = rng.standard_normal((b, n, n))
+    a = w @ np.transpose(w, (0, 2, 1)) / n + np.eye(n)
+    rhs = rng.standard_normal((b, n))
+    d = m.factor_batched("gmw81", a, mode="strict")
+    x = m.solve_batched(d, rhs)
+    for i in range(b):
+        ae = a[i] + np.diag(d.e[i])
+        assert np.abs(ae @ x[i] - rhs[i]).max() <= 1e-9 * np.abs(ae).max() * max(np.abs(x[i]).max(), 1.0)
+    xf = m.factor_solve_batched("gmw81", a, rhs, mode="strict")
+    assert np.array_equal(xf, x)
+
+
+def test_torch_arguments_are_checked(torch_cuda):
+    """Device pointers are reinterpreted as f64 / u64 device memory by the kernels: wrong dtype,
+    host tensors next to device tensors and mismatched shapes must raise, not fault."""
+    torch = torch_cuda
+    a = torch.from_numpy(matgen.make("pd", 3, 8, 16)).cuda()
+    d = m.factor_batched("se99", a)
+    rhs = torch.ones((8, 16), dtype=torch.float64, device="cuda")
+    with pytest.raises(TypeError):
+        m.factor_batched("se99", a.float())
+    with pytest.raises(TypeError):
+        m.solve_batched(d, rhs.float())
+    with pytest.raises((ValueError, TypeError)):
+        m.solve_batched(m.Decomposition(d.l.cpu(), d.e, d.p), rhs)
+    with pytest.raises(ValueError):
+        m.solve_batched(m.Decomposition(d.l[:4], d.e, d.p), rhs)
+    with pytest.raises(TypeError):
+        m.gershgorin_circles_batched(a.float())
+    with pytest.raises((ValueError, TypeError)):
+        m.verify_batched(a, m.Decomposition(d.l, d.e.cpu(), d.p))
+    with pytest.raises((ValueError, TypeError)):
+        m.factor_solve_batched("se99", a, rhs.cpu())
+    with pytest.raises(ValueError):
+        m.factor_solve_batched("se99", a, rhs[:4])
+    x = m.solve_batched(d, rhs)          # and the well-formed call still works
+    assert x.shape == rhs.shape
+
+
+def test_zz_report_relaxed_bar_counts():
+    """Not a check: prints how many FAST-mode comparisons of this session used one of the two
+    GMW81-only relaxed bars of _assert_tolerance (run pytest with -s to see it)."""
+    print(f"\n[parity] FAST-mode matrices checked: {RELAXED['checked']}, "
+          f"E bar relaxed (GMW81, ||E|| < 1e-4 ||A||): {RELAXED['e_relaxed']}, "
+          f"reconstruction bar relaxed (GMW81, ||A+E|| > 1e3 ||A||): {RELAXED['recon_relaxed']}")
