@@ -1,0 +1,39 @@
+// bsm_inst.cu -- instantiates the blocked large-n kernels (bsm_kernels.cuh) and their launcher.
+#include <cstdlib>
+
+#include "bsm_kernels.cuh"
+#include "launch_cache.cuh"
+#include "warp_kernels.cuh"
+
+namespace modchol {
+
+template <int kThreads, int KB>
+static cudaError_t launch_bsm_gmw(int n, long long batch, const double* a, double* l, double* e,
+                                  unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    auto kern = bsm_gmw_kernel<kThreads, KB>;
+    const size_t smem = bsm_smem_doubles(n, KB) * sizeof(double);
+    const size_t smem_max = bsm_smem_doubles(kThreads, KB) * sizeof(double);
+    int occ = 1;
+    cudaError_t ce = cached_occupancy(kern, kThreads, smem, smem_max, &occ);
+    if (ce != cudaSuccess) return ce;
+    long long blocks = batch;
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;   // persistent: every block strides over the batch
+    kern<<<(unsigned)blocks, kThreads, smem, st>>>(n, batch, a, l, e, p, k);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bsm_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
+                              unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    if (algo != kGMW81)
+        return cudaErrorNotSupported;
+    if (n <= 256)
+        return launch_bsm_gmw<256, 16>(n, batch, a, l, e, p, k, sms, st);
+    if (n <= 512)
+        return launch_bsm_gmw<512, 32>(n, batch, a, l, e, p, k, sms, st);
+    return launch_bsm_gmw<1024, 16>(n, batch, a, l, e, p, k, sms, st);
+}
+
+}  // namespace modchol

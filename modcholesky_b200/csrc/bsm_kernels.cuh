@@ -1,0 +1,451 @@
+// bsm_kernels.cuh -- FAST-mode blocked (panel) kernels for the LARGE size class, 128 < n <= 1024:
+// one thread block per matrix, thread = permuted position (row), physical pivoting, the working
+// matrix resident in L2 / HBM and the current column PANEL in shared memory.
+//
+//   for each panel of KB columns [j0, j0 + KB):
+//       for j in the panel (left-looking inside the panel, gmw81.rs:70-111 / se9x phase loops):
+//           pivot search on the per-row scalars (running diagonal / Gershgorin bound) -- the
+//               scalars are brought up to date at every step, so every pivot, theta, norm and
+//               E decision sees current values although the trailing matrix is only updated at
+//               panel boundaries;
+//           symmetric exchange j <-> m: finished rows of L, panel rows, trailing matrix, scalars;
+//           column j = T(j.., j) - P(j.., 0..c) P(j, 0..c)^T   (T: one coalesced row of the
+//               transposed trailing storage, brought in by ONE bulk-copy (TMA) instruction and an
+//               mbarrier; P: shared memory, conflict free);
+//           scale, append as panel column c, update the scalars
+//       write the panel's rows of L (64 / 128 / 256-byte row segments)
+//       trailing update T -= P P^T of the shrinking trailing block on the FP64 tensor pipe
+//           (mma.sync.m8n8k4.f64, KB/4 per 8x8 tile), tiles streamed from L2 with 128-bit
+//           accesses, every warp of the block on its own block rows.
+//
+// Storage: the working matrix lives IN PLACE in the caller's output buffer -- no scratch.  The
+// strictly lower trailing part T(i,k), i > k, is kept TRANSPOSED in the strict upper triangle,
+// l[k n + i] (the symmetric input delivers it as is: a[k][i] = a[i][k]), so that a pivot column
+// is a contiguous row segment; its diagonal lives in shared memory; finished L entries go to
+// the lower triangle (final place).  The strict upper triangle is zeroed at the end
+// (gmw81.rs:112-125 / se99.rs:189-192).
+//
+// Flops: n^3/3 (the trailing block shrinks, unlike the implicit-pivoting small-n kernels whose
+// fixed tiles would cost 3x here); L2/HBM traffic of the updates: ~ n^3 / (3 KB) * 16 bytes.
+#pragma once
+#include "wip_kernels.cuh"
+
+namespace modchol {
+
+constexpr int kBsmMaxWarps = 32;
+
+// panel column stride (doubles): >= n rounded up to 8, == 4 (mod 16): the per-step column
+// write (thread = row) and the DMMA fragment loads are both conflict free
+__host__ __device__ inline int bsm_ldp(int n)
+{
+    int l = (n + 7) & ~7;
+    while ((l & 15) != 4)
+        l += 4;
+    return l;
+}
+// doubles of dynamic shared memory: panel + diagonal + column line + exchange scratch + mbarrier
+__host__ __device__ inline size_t bsm_smem_doubles(int n, int kb)
+{
+    return (size_t)kb * bsm_ldp(n) + 2 * (size_t)((n + 7) & ~7) + 3 * 2 * kBsmMaxWarps + 16 + 2;
+}
+
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+struct BsmScratch {
+    unsigned base;   // byte address: [2][3][32] words (hi, lo, pos), then [2][32] doubles, then 8 doubles
+    int buf;
+};
+
+// first maximum by position of v over the candidate threads (utils.rs:52-91): position of the
+// winner (`lo` when there is no candidate); ONE __syncthreads
+__device__ __forceinline__ int bsm_argmax_first(BsmScratch& sc, int nwarps, double v, bool cand, int pos, int lo,
+                                                double& best)
+{
+    int khi;
+    unsigned klo;
+    wip_key(v, khi, klo);
+    cand = cand && v == v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wh = __reduce_max_sync(kFull, cand ? khi : (int)0x80000000);
+    const bool c1 = cand && khi == wh;
+    const unsigned wl = __reduce_max_sync(kFull, c1 ? klo : 0u);
+    const unsigned wp = __reduce_min_sync(kFull, (c1 && klo == wl) ? (unsigned)pos : 0xffffu);
+    const unsigned a = sc.base + 4u * (unsigned)(sc.buf * 96);
+    if (lane == 0) {
+        sts_u32(a + 4u * warp, (unsigned)wh);
+        sts_u32(a + 4u * (32 + warp), wl);
+        sts_u32(a + 4u * (64 + warp), wp);
+    }
+    __syncthreads();
+    const bool in = lane < nwarps;
+    const int h = in ? (int)lds_u32(a + 4u * lane) : (int)0x80000000;
+    const unsigned l = in ? lds_u32(a + 4u * (32 + lane)) : 0u;
+    const unsigned p = in ? lds_u32(a + 4u * (64 + lane)) : 0xffffu;
+    const int gh = __reduce_max_sync(kFull, h);
+    const bool g1 = h == gh;
+    const unsigned gl = __reduce_max_sync(kFull, g1 ? l : 0u);
+    const unsigned gp = __reduce_min_sync(kFull, (g1 && l == gl) ? p : 0xffffu);
+    sc.buf ^= 1;
+    const int m = gh;
+    best = (m == (int)0x80000000) ? -INFINITY
+                                  : __hiloint2double(m ^ ((m >> 31) & 0x7fffffff), (int)(gl ^ (unsigned)(m >> 31)));
+    return (gh == (int)0x80000000 || gp >= 0xffffu) ? lo : (int)gp;
+}
+
+// block-wide maximum (kMax) / minimum of v over the candidate threads, NaN never taken, `none`
+// without candidates; ONE __syncthreads
+template <bool kMax>
+__device__ __forceinline__ double bsm_extreme(BsmScratch& sc, int nwarps, double v, bool cand, double none)
+{
+    int khi;
+    unsigned klo;
+    wip_key(v, khi, klo);
+    cand = cand && v == v;
+    if (!kMax) {
+        khi = ~khi;
+        klo = ~klo;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wh = __reduce_max_sync(kFull, cand ? khi : (int)0x80000000);
+    const unsigned wl = __reduce_max_sync(kFull, (cand && khi == wh) ? klo : 0u);
+    const unsigned a = sc.base + 4u * (unsigned)(sc.buf * 96);
+    if (lane == 0) {
+        sts_u32(a + 4u * warp, (unsigned)wh);
+        sts_u32(a + 4u * (32 + warp), wl);
+    }
+    __syncthreads();
+    const bool in = lane < nwarps;
+    const int h = in ? (int)lds_u32(a + 4u * lane) : (int)0x80000000;
+    const unsigned l = in ? lds_u32(a + 4u * (32 + lane)) : 0u;
+    int gh = __reduce_max_sync(kFull, h);
+    unsigned gl = __reduce_max_sync(kFull, h == gh ? l : 0u);
+    sc.buf ^= 1;
+    if (gh == (int)0x80000000)
+        return none;
+    if (!kMax) {
+        gh = ~gh;
+        gl = ~gl;
+    }
+    return __hiloint2double(gh ^ ((gh >> 31) & 0x7fffffff), (int)(gl ^ (unsigned)(gh >> 31)));
+}
+
+// block-wide sum (tree order inside the warps, DMMA across them); ONE __syncthreads
+__device__ __forceinline__ double bsm_sum(BsmScratch& sc, int nwarps, double x)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = wip_sum32(x);
+    const unsigned a = sc.base + 4u * 192u + 8u * (unsigned)(sc.buf * 32);
+    if (lane == 0)
+        sts_f64(a + 8u * warp, x);
+    __syncthreads();
+    const double y = lane < nwarps ? lds_f64(a + 8u * lane) : 0.0;
+    sc.buf ^= 1;
+    return wip_sum32(y);
+}
+
+// ---- mbarrier + bulk copy (TMA, non-tensor form) ------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+        :: "r"(mbar), "r"(parity) : "memory");
+}
+// generic-proxy writes (st.global / st.shared) before, async-proxy (bulk copy) accesses after
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// Trailing update T(i,k) -= sum_c P(i,c) P(k,c) for j1 <= k < i < n, T(i,k) stored at Lb[k n + i],
+// and the same for the diagonal td[i] (shared memory).  Tile (bj, bi), bi >= bj, is held
+// transposed: fragment rows = k in block bj (A fragment: lane l holds P(8 bj + l/4, 4 h + l%4)),
+// fragment columns = i in block bi (B fragment: P(8 bi + l/4, 4 h + l%4)), accumulator
+// C[l/4][2 (l%4) + {0,1}] = T(8 bi + 2 (l%4) + {0,1}, 8 bj + l/4): two doubles contiguous in i.
+// Each warp takes the block rows bi = b0 + warp, + nwarps, ... (cyclic: balanced to within one
+// row), keeps the row's B fragments in registers and streams the tiles with 128-bit accesses.
+template <int KB>
+__device__ __forceinline__ void bsm_trailing_update(double* __restrict__ Lb, int n, int j1, unsigned pb, int ldp,
+                                                    unsigned tdb, bool wide)
+{
+    constexpr int KC = KB / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int r8 = lane >> 2, c4 = lane & 3;
+    const int b0 = j1 >> 3, nb = (n + 7) >> 3;
+    const unsigned pf = pb + 8u * (unsigned)(c4 * ldp + r8);   // P(r8, c4)
+    for (int bi = b0 + warp; bi < nb; bi += nwarps) {
+        double fb[KC];
+#pragma unroll
+        for (int h = 0; h < KC; ++h)
+            fb[h] = lds_f64(pf + 8u * (unsigned)(4 * h * ldp + 8 * bi));
+        const int i0 = 8 * bi + 2 * c4;
+        const bool full_i = 8 * bi + 7 < n;
+        int bj = b0;
+        // interior tiles (bj < bi, all rows and columns inside the matrix), four at a time: the
+        // four 128-bit loads are in flight together, so a warp pays one L2 round trip per group
+        if (full_i && wide) {
+            for (; bj + 4 <= bi; bj += 4) {
+                double2 v[4];
+                double* tp = Lb + (size_t)(8 * bj + r8) * n + i0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = *reinterpret_cast<const double2*>(tp + (size_t)(8 * u) * n);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int h = 0; h < KC; ++h) {
+                        const double fa = wip_neg(lds_f64(pf + 8u * (unsigned)(4 * h * ldp + 8 * (bj + u))));
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                     : "+d"(v[u].x), "+d"(v[u].y) : "d"(fa), "d"(fb[h]));
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<double2*>(tp + (size_t)(8 * u) * n) = v[u];
+            }
+        }
+        for (; bj <= bi; ++bj) {
+            const int k = 8 * bj + r8;
+            double* tp = Lb + (size_t)k * n + i0;
+            const bool interior = bj < bi && full_i;   // warp-uniform; (bj < bi => k-block is full too)
+            double c0, c1;
+            if (interior && wide) {
+                const double2 v = *reinterpret_cast<const double2*>(tp);
+                c0 = v.x;
+                c1 = v.y;
+            } else {
+                c0 = (k < n && i0 < n && i0 > k) ? tp[0] : 0.0;
+                c1 = (k < n && i0 + 1 < n && i0 + 1 > k) ? tp[1] : 0.0;
+                if (bj == bi) {   // the diagonal entries of T live in shared memory
+                    if (i0 == k && k < n) c0 = lds_f64(tdb + 8u * (unsigned)k);
+                    if (i0 + 1 == k && k < n) c1 = lds_f64(tdb + 8u * (unsigned)k);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < KC; ++h) {
+                const double fa = wip_neg(lds_f64(pf + 8u * (unsigned)(4 * h * ldp + 8 * bj)));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(c0), "+d"(c1) : "d"(fa), "d"(fb[h]));
+            }
+            if (interior && wide) {
+                *reinterpret_cast<double2*>(tp) = make_double2(c0, c1);
+            } else {
+                if (k < n && i0 < n && i0 > k) tp[0] = c0;
+                if (k < n && i0 + 1 < n && i0 + 1 > k) tp[1] = c1;
+                if (bj == bi) {
+                    if (i0 == k && k < n) sts_f64(tdb + 8u * (unsigned)k, c0);
+                    if (i0 + 1 == k && k < n) sts_f64(tdb + 8u * (unsigned)k, c1);
+                }
+            }
+        }
+    }
+}
+
+// GMW81 (gmw81.rs:39-134), symmetric FAST form (see wsm_gmw.cuh): L entries are c_is / sqrt(d_s).
+template <int kThreads, int KB>
+__global__ void __launch_bounds__(kThreads)
+bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
+               double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nwarps = kThreads >> 5;
+    const int ldp = bsm_ldp(n);
+    const int npad = (n + 7) & ~7;
+    const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
+    const unsigned pb = smb;                                        // panel: column c at pb + 8 c ldp
+    const unsigned tdb = pb + 8u * (unsigned)(KB * ldp);            // diagonal of T, by position
+    const unsigned lineb = tdb + 8u * (unsigned)npad;               // pivot column, staged by bulk copy
+    BsmScratch sc;
+    sc.base = lineb + 8u * (unsigned)npad;
+    sc.buf = 0;
+    const unsigned scalb = sc.base + 4u * 192u + 8u * 64u;          // 8 doubles of scalars
+    const unsigned mbar = scalb + 8u * 8u;                          // one mbarrier
+    const size_t nn = (size_t)n * n;
+    const int row = tid;
+    const bool rv = row < n;
+    // 128-bit tile accesses / bulk copies need 16-byte aligned rows
+    const bool wide = (n & 1) == 0 && (((size_t)L) & 15) == 0;
+    if (tid == 0)
+        mbar_init(mbar, 1);
+    unsigned phase = 0;
+    __syncthreads();
+
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const double* Ab = A + (size_t)b * nn;
+        double* Lb = L + (size_t)b * nn;
+        // ---- in: the strict upper triangle of A is T transposed; diagonal to shared memory;
+        // off-diagonal maximum on the fly (gmw81.rs:52-58) ------------------------------------
+        double om = 0.0;
+        for (int k = tid >> 5; k < n; k += nwarps) {   // one row per warp: coalesced
+            for (int i = k + 1 + lane; i < n; i += 32) {
+                const double v = __ldg(Ab + (size_t)k * n + i);
+                Lb[(size_t)k * n + i] = v;
+                om = fmax(om, fabs(v));
+            }
+        }
+        double cd = rv ? __ldg(Ab + (size_t)row * (n + 1)) : 0.0;   // running diagonal (gmw81.rs:66-67)
+        if (row < npad)
+            sts_f64(tdb + 8u * (unsigned)row, cd);
+        double ev = 0.0;
+        int perm = row;
+        const double diag_max = bsm_extreme<true>(sc, nwarps, fabs(cd), rv, 0.0);
+        const double off_max = bsm_extreme<true>(sc, nwarps, om, true, 0.0);
+        const double nf = (double)n;
+        const double delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(diag_max, off_max)));
+        const double beta =
+            dsqrt(fmax(fmax(diag_max, ddiv(off_max, dsqrt(dsub(dmul(nf, nf), 1.0)))), MODCHOL_EPS));
+        const double rbeta = ddiv(1.0, beta);
+        fence_proxy_async();
+        __syncthreads();   // T is in place (block-scope visibility of the global stores)
+
+        for (int j0 = 0; j0 < n; j0 += KB) {
+            const int jend = min(n, j0 + KB);
+            // panel rows of finished positions and columns not yet produced must read as zero in
+            // the trailing update: clear the panel
+            for (int q = tid; q < KB * ldp; q += kThreads)
+                sts_f64(pb + 8u * (unsigned)q, 0.0);
+            __syncthreads();
+            for (int j = j0; j < jend; ++j) {
+                const int c = j - j0;
+                // ---- pivot on max |c_ii| (gmw81.rs:71-78) ----------------------------------------
+                double best;
+                const int m = bsm_argmax_first(sc, nwarps, fabs(cd), rv && row >= j, row, j, best);
+                // ---- symmetric exchange j <-> m (utils.rs:30-49) fused with the read of column j:
+                // the exchange loads T(i,j) and T(i,m) anyway and the new column j IS the old column
+                // m, so a step costs ONE round trip to L2; the stores are not waited for (the next
+                // reader of those locations sits behind a barrier)
+                double col = 0.0;
+                if (m != j) {
+                    double x = 0.0, y = 0.0, lx = 0.0, ly = 0.0;
+                    double *a1 = nullptr, *a2 = nullptr;
+                    const bool tsw = rv && row > j && row != m;
+                    if (tsw) {                                          // T(i,j) <-> T(m,i) | T(i,m)
+                        a1 = Lb + (size_t)j * n + row;
+                        a2 = row < m ? Lb + (size_t)row * n + m : Lb + (size_t)m * n + row;
+                        x = *a1;
+                        y = *a2;
+                    } else if (row == m) {
+                        y = Lb[(size_t)j * n + m];                      // T(m,j) stays where it is
+                    }
+                    const bool lsw = tid < j0;                          // L(j, 0..j0) <-> L(m, 0..j0)
+                    if (lsw) {
+                        lx = Lb[(size_t)j * n + tid];
+                        ly = Lb[(size_t)m * n + tid];
+                    }
+                    if (row == j || row == m) {                         // scalars through shared memory
+                        const unsigned q = scalb + (row == j ? 0u : 16u);
+                        sts_f64(q, cd);
+                        sts_f64(q + 8, (double)perm);
+                    }
+                    if (tid < c) {                                      // panel rows j, m
+                        const unsigned q = pb + 8u * (unsigned)(tid * ldp);
+                        const double u = lds_f64(q + 8u * j), w = lds_f64(q + 8u * m);
+                        sts_f64(q + 8u * j, w);
+                        sts_f64(q + 8u * m, u);
+                    }
+                    if (tid == 32) {                                    // diagonal of T
+                        const double u = lds_f64(tdb + 8u * j), w = lds_f64(tdb + 8u * m);
+                        sts_f64(tdb + 8u * j, w);
+                        sts_f64(tdb + 8u * m, u);
+                    }
+                    if (tsw) {
+                        *a1 = y;
+                        *a2 = x;
+                    }
+                    if (lsw) {
+                        Lb[(size_t)j * n + tid] = ly;
+                        Lb[(size_t)m * n + tid] = lx;
+                    }
+                    col = y;
+                    __syncthreads();
+                    if (row == j || row == m) {
+                        const unsigned q = scalb + (row == j ? 16u : 0u);
+                        cd = lds_f64(q);
+                        perm = (int)lds_f64(q + 8);
+                    }
+                } else if (rv && row > j) {
+                    col = Lb[(size_t)j * n + row];
+                }
+                if (row == j)
+                    col = lds_f64(tdb + 8u * (unsigned)j);      // c_jj from the same updates
+                // left-looking inside the panel: minus P(i, 0..c) . P(j, 0..c)
+                if (rv && row >= j) {
+                    unsigned q = pb;
+#pragma unroll 4
+                    for (int t = 0; t < c; ++t, q += 8u * (unsigned)ldp)
+                        col = __fma_rn(-lds_f64(q + 8u * (unsigned)row), lds_f64(q + 8u * (unsigned)j), col);
+                }
+                if (row == j)
+                    sts_f64(scalb + 32u, col);
+                // theta = max_{i>j} |c_ij| (gmw81.rs:87-100); c_jj rides on the same barrier
+                const double theta = bsm_extreme<true>(sc, nwarps, fabs(col), rv && row > j, 0.0);
+                const double cjj = lds_f64(scalb + 32u);
+                const double tb = dmul(theta, rbeta);
+                const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
+                double y = rsqrt_normal(dj);
+                double sq = dmul(dj, y);
+                if (!fast_range_ok(dj))
+                    wip_slow_gmw(dj, sq, y);
+                const double ls = dmul(col, y);
+                if (rv && row >= j)
+                    sts_f64(pb + 8u * (unsigned)(c * ldp + row), row == j ? sq : ls);
+                if (rv && row > j)
+                    cd = __fma_rn(-ls, ls, cd);                     // gmw81.rs:104-109
+                if (row == j)
+                    ev = dsub(dj, cjj);                             // gmw81.rs:110
+                __syncthreads();
+            }
+            // ---- the panel's columns of L: row i gets L(i, j0 .. min(i, jend-1)) ----------------
+            if (rv && row >= j0) {
+                const int cnt = min(jend - j0, row - j0 + 1);
+                double* dst = Lb + (size_t)row * n + j0;
+                for (int t = 0; t < cnt; ++t)
+                    dst[t] = lds_f64(pb + 8u * (unsigned)(t * ldp + row));
+            }
+            // (rows inside the panel are finished and lie outside the blocks the update touches:
+            // jend is a multiple of 8)
+            if (jend < n)
+                bsm_trailing_update<KB>(Lb, n, jend, pb, ldp, tdb, wide);
+            fence_proxy_async();
+            __syncthreads();
+        }
+
+        // ---- out: strict upper triangle zero (gmw81.rs:112-125), e un-permuted, p ---------------
+        for (int k = tid >> 5; k < n; k += nwarps)
+            for (int i = k + 1 + lane; i < n; i += 32)
+                Lb[(size_t)k * n + i] = 0.0;
+        if (rv) {
+            E[(size_t)b * n + perm] = ev;                               // gmw81.rs:127-131
+            P[(size_t)b * n + row] = (unsigned long long)perm;
+        }
+        if (K && tid == 0)
+            K[b] = -1;
+        __syncthreads();
+    }
+}
+
+}  // namespace modchol

@@ -204,7 +204,7 @@ int slot_reserve(Slot& s, size_t mats, int n)
 }
 
 // ---- size-class dispatch ---------------------------------------------------------------
-enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3, kClsCtaPacked = 4 };
+enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3, kClsCtaPacked = 4, kClsCtaBlocked = 5 };
 
 // Which small-n family serves n <= 32 (0 auto, 1 registers, 2 shared memory); initialised
 // from MODCHOL_SMALL_KERNEL=reg|wsm, changed by modchol_set_small_kernel_family().
@@ -222,6 +222,16 @@ int small_kernel_pref()
 
 int cta_ld(int n) { return (n & 1) ? n : n + 1; }
 
+// smallest n served by the blocked large-n kernels (MODCHOL_BSM_MIN, tuning knob)
+int bsm_min_n()
+{
+    static const int v = [] {
+        const char* e = getenv("MODCHOL_BSM_MIN");
+        return e ? atoi(e) : 257;
+    }();
+    return v;
+}
+
 KernelClass classify(int algo, int mode, int n, int smem_optin)
 {
     const bool reg_ok = warp_kernel_available(algo, mode, n);
@@ -236,6 +246,8 @@ KernelClass classify(int algo, int mode, int n, int smem_optin)
         return kClsWarpSmem;
     if (reg_ok)
         return kClsWarp;
+    if (bsm_kernel_available(algo, mode, n) && n >= bsm_min_n())
+        return kClsCtaBlocked;
     if (csm_kernel_available(algo, mode, n))
         return kClsCtaPacked;
     if (smem_optin <= 0)
@@ -293,6 +305,13 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
         g_launches.fetch_add(1);
         if (ce != cudaSuccess)
             return fail(MODCHOL_ERR_CUDA, "wsm kernel launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    if (cls == kClsCtaBlocked) {
+        cudaError_t ce = launch_bsm_kernel(algo, n, batch, a, l, e, p, k, c.sms, st);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "bsm kernel launch failed: %s", cudaGetErrorString(ce));
         return MODCHOL_OK;
     }
     if (cls == kClsCtaPacked) {
@@ -511,6 +530,7 @@ const char* modchol_kernel_class(int algo, int mode, int32_t n)
     case kClsWarp: return "warp32";
     case kClsWarpSmem: return "warp_smem";
     case kClsCtaPacked: return "cta_packed";
+    case kClsCtaBlocked: return "cta_blocked";
     case kClsCtaSmem: return "cta_smem";
     default: return "cta_gmem";
     }

@@ -106,6 +106,15 @@ inline cudaError_t launch_csm_kernel(int algo, int mode, int n, long long batch,
     return cudaErrorNotSupported;
 }
 
+// blocked large-n kernels (bsm_kernels.cuh), FAST mode, 128 < n <= 1024; defined in bsm_inst.cu
+constexpr int kBsmMaxN = 1024;
+cudaError_t launch_bsm_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
+                              unsigned long long* p, int* k, int sms, cudaStream_t st);
+inline bool bsm_kernel_available(int algo, int mode, int n)
+{
+    return mode == 1 && algo == 0 && n > 128 && n <= kBsmMaxN;
+}
+
 inline cudaError_t launch_warp_kernel(int algo, int mode, int n, long long batch, const double* a,
                                       double* l, double* e, unsigned long long* p, int* k, int sms,
                                       cudaStream_t st)
