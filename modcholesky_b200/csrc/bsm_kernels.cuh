@@ -265,8 +265,8 @@ __device__ __forceinline__ void bsm_trailing_update(double* __restrict__ Lb, int
 }
 
 // GMW81 (gmw81.rs:39-134), symmetric FAST form (see wsm_gmw.cuh): L entries are c_is / sqrt(d_s).
-template <int kThreads, int KB>
-__global__ void __launch_bounds__(kThreads)
+template <int kThreads, int KB, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
                double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
 {
@@ -337,88 +337,107 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
                 // ---- symmetric exchange j <-> m (utils.rs:30-49) fused with the read of column j:
                 // the exchange loads T(i,j) and T(i,m) anyway and the new column j IS the old column
                 // m, so a step costs ONE round trip to L2; the stores are not waited for (the next
-                // reader of those locations sits behind a barrier)
-                double col = 0.0;
-                if (m != j) {
-                    double x = 0.0, y = 0.0, lx = 0.0, ly = 0.0;
-                    double *a1 = nullptr, *a2 = nullptr;
-                    const bool tsw = rv && row > j && row != m;
-                    if (tsw) {                                          // T(i,j) <-> T(m,i) | T(i,m)
-                        a1 = Lb + (size_t)j * n + row;
-                        a2 = row < m ? Lb + (size_t)row * n + m : Lb + (size_t)m * n + row;
-                        x = *a1;
-                        y = *a2;
-                    } else if (row == m) {
-                        y = Lb[(size_t)j * n + m];                      // T(m,j) stays where it is
-                    }
-                    const bool lsw = tid < j0;                          // L(j, 0..j0) <-> L(m, 0..j0)
-                    if (lsw) {
-                        lx = Lb[(size_t)j * n + tid];
-                        ly = Lb[(size_t)m * n + tid];
-                    }
-                    if (row == j || row == m) {                         // scalars through shared memory
-                        const unsigned q = scalb + (row == j ? 0u : 16u);
-                        sts_f64(q, cd);
-                        sts_f64(q + 8, (double)perm);
-                    }
-                    if (tid < c) {                                      // panel rows j, m
-                        const unsigned q = pb + 8u * (unsigned)(tid * ldp);
-                        const double u = lds_f64(q + 8u * j), w = lds_f64(q + 8u * m);
-                        sts_f64(q + 8u * j, w);
-                        sts_f64(q + 8u * m, u);
-                    }
-                    if (tid == 32) {                                    // diagonal of T
-                        const double u = lds_f64(tdb + 8u * j), w = lds_f64(tdb + 8u * m);
-                        sts_f64(tdb + 8u * j, w);
-                        sts_f64(tdb + 8u * m, u);
-                    }
-                    if (tsw) {
-                        *a1 = y;
-                        *a2 = x;
-                    }
-                    if (lsw) {
-                        Lb[(size_t)j * n + tid] = ly;
-                        Lb[(size_t)m * n + tid] = lx;
-                    }
+                // reader of those locations sits behind a barrier).  Nothing in shared memory moves
+                // before the column is evaluated -- rows j and m of the panel and of the diagonal
+                // are read through `prow` / `pj` -- so the exchange needs no barrier of its own.
+                const bool swp = m != j;
+                const int pj = m;                                   // old place of the new row j
+                const int prow = (swp && row == j) ? m : ((swp && row == m) ? j : row);
+                double col = 0.0, x = 0.0, y = 0.0, lx = 0.0, ly = 0.0;
+                double *a1 = nullptr, *a2 = nullptr;
+                const bool tsw = swp && rv && row > j && row != m;
+                const bool lsw = swp && tid < j0;                   // L(j, 0..j0) <-> L(m, 0..j0)
+                if (tsw) {                                          // T(i,j) <-> T(m,i) | T(i,m)
+                    a1 = Lb + (size_t)j * n + row;
+                    a2 = row < m ? Lb + (size_t)row * n + m : Lb + (size_t)m * n + row;
+                    x = *a1;
+                    y = *a2;
                     col = y;
-                    __syncthreads();
+                } else if (rv && row > j) {
+                    col = Lb[(size_t)j * n + row];                  // no exchange, or T(m,j), which stays
+                }
+                if (lsw) {
+                    lx = Lb[(size_t)j * n + tid];
+                    ly = Lb[(size_t)m * n + tid];
+                }
+                if (swp && (row == j || row == m)) {                // scalars through shared memory
+                    const unsigned q = scalb + (row == j ? 0u : 16u);
+                    sts_f64(q, cd);
+                    sts_f64(q + 8, (double)perm);
+                }
+                if (row == j)
+                    col = lds_f64(tdb + 8u * (unsigned)pj);         // c_jj from the same updates
+                // left-looking inside the panel: minus P(i, 0..c) . P(j, 0..c), accumulated apart
+                // from the loaded element so that the products overlap the round trip to L2
+                if (rv && row >= j) {
+                    const double* pr = sm + prow;                   // panel column t at sm + t ldp
+                    const double* pq = sm + pj;
+                    double s0 = 0.0, s1 = 0.0;
+                    int t = 0;
+                    for (; t + 4 <= c; t += 4) {
+                        const double r0 = pr[(t + 0) * ldp], r1 = pr[(t + 1) * ldp];
+                        const double r2 = pr[(t + 2) * ldp], r3 = pr[(t + 3) * ldp];
+                        const double q0 = pq[(t + 0) * ldp], q1 = pq[(t + 1) * ldp];
+                        const double q2 = pq[(t + 2) * ldp], q3 = pq[(t + 3) * ldp];
+                        s0 = __fma_rn(r0, q0, s0);
+                        s1 = __fma_rn(r1, q1, s1);
+                        s0 = __fma_rn(r2, q2, s0);
+                        s1 = __fma_rn(r3, q3, s1);
+                    }
+                    for (; t < c; ++t)
+                        s0 = __fma_rn(pr[t * ldp], pq[t * ldp], s0);
+                    col = dsub(col, dadd(s0, s1));
+                }
+                if (row == j)
+                    sts_f64(scalb + 32u, col);
+                if (tsw) {
+                    *a1 = y;
+                    *a2 = x;
+                }
+                if (lsw) {
+                    Lb[(size_t)j * n + tid] = ly;
+                    Lb[(size_t)m * n + tid] = lx;
+                }
+                // theta = max_{i>j} |c_ij| (gmw81.rs:87-100); c_jj rides on the same barrier
+                const double theta = bsm_extreme<true>(sc, nwarps, fabs(col), rv && row > j, 0.0);
+                const double cjj = lds_f64(scalb + 32u);
+                if (swp) {
+                    // now the shared-memory side of the exchange (every reader of the old places is
+                    // past the barrier): scalars, panel rows j and m, diagonal of T
                     if (row == j || row == m) {
                         const unsigned q = scalb + (row == j ? 16u : 0u);
                         cd = lds_f64(q);
                         perm = (int)lds_f64(q + 8);
                     }
-                } else if (rv && row > j) {
-                    col = Lb[(size_t)j * n + row];
+                    if (tid < c) {
+                        const unsigned q = pb + 8u * (unsigned)(tid * ldp);
+                        const double u = lds_f64(q + 8u * j), w = lds_f64(q + 8u * m);
+                        sts_f64(q + 8u * j, w);
+                        sts_f64(q + 8u * m, u);
+                    }
+                    if (tid == 32) {
+                        const double u = lds_f64(tdb + 8u * j), w = lds_f64(tdb + 8u * m);
+                        sts_f64(tdb + 8u * j, w);
+                        sts_f64(tdb + 8u * m, u);
+                    }
                 }
-                if (row == j)
-                    col = lds_f64(tdb + 8u * (unsigned)j);      // c_jj from the same updates
-                // left-looking inside the panel: minus P(i, 0..c) . P(j, 0..c)
-                if (rv && row >= j) {
-                    unsigned q = pb;
-#pragma unroll 4
-                    for (int t = 0; t < c; ++t, q += 8u * (unsigned)ldp)
-                        col = __fma_rn(-lds_f64(q + 8u * (unsigned)row), lds_f64(q + 8u * (unsigned)j), col);
-                }
-                if (row == j)
-                    sts_f64(scalb + 32u, col);
-                // theta = max_{i>j} |c_ij| (gmw81.rs:87-100); c_jj rides on the same barrier
-                const double theta = bsm_extreme<true>(sc, nwarps, fabs(col), rv && row > j, 0.0);
-                const double cjj = lds_f64(scalb + 32u);
                 const double tb = dmul(theta, rbeta);
                 const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
-                double y = rsqrt_normal(dj);
-                double sq = dmul(dj, y);
+                double yy = rsqrt_normal(dj);
+                double sq = dmul(dj, yy);
                 if (!fast_range_ok(dj))
-                    wip_slow_gmw(dj, sq, y);
-                const double ls = dmul(col, y);
+                    wip_slow_gmw(dj, sq, yy);
+                const double ls = dmul(col, yy);
                 if (rv && row >= j)
                     sts_f64(pb + 8u * (unsigned)(c * ldp + row), row == j ? sq : ls);
                 if (rv && row > j)
                     cd = __fma_rn(-ls, ls, cd);                     // gmw81.rs:104-109
                 if (row == j)
                     ev = dsub(dj, cjj);                             // gmw81.rs:110
-                __syncthreads();
+                // no barrier here: the next step's pivot search has one between these writes and
+                // their first readers
             }
+            __syncthreads();
             // ---- the panel's columns of L: row i gets L(i, j0 .. min(i, jend-1)) ----------------
             if (rv && row >= j0) {
                 const int cnt = min(jend - j0, row - j0 + 1);

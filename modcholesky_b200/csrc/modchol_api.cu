@@ -227,7 +227,7 @@ int bsm_min_n()
 {
     static const int v = [] {
         const char* e = getenv("MODCHOL_BSM_MIN");
-        return e ? atoi(e) : 257;
+        return e ? atoi(e) : 129;   // measured: ahead of the packed kernels from n = 136 on (GMW81)
     }();
     return v;
 }
