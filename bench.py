@@ -16,6 +16,12 @@ e2e      : the same metric through the public API with HOST (pinned) buffers: th
            stages host -> device -> host in overlapped chunks inside the timed region.
 roofline : algorithmic bytes (16 n^2 + 16 n per matrix) / kernel time,
            against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+configs  : (N = 1 only) short timed runs of the other BASELINE.json configs -- configs[0] the
+           reference's own single-matrix bench shapes (CPU oracle us/call and the GPU batch = 1
+           call latency), configs[1] 2^20 x 16^2 SE99, configs[2] 200 000 x 64^2 SE90, configs[3]
+           4 096 x 256^2 GMW81 (with the FP64-pipe fraction against the DFMA / DMMA peaks the
+           library measures on this device) -- plus the reference's bench family (Q D Q^T,
+           12 / 128 / 256, assembled on the device) and the on-device verifier.
 cpu_baseline : the CPU oracle (a C restatement of the reference; the Rust crate cannot be
            built here) looped over a bounded sample on all host cores, rank 0, N = 1 only.
 """
@@ -112,13 +118,155 @@ def measured_peak():
 
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu capture, scaled to
-    this batch (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        t = json.load(open(p))
-        return t["dram_bytes_per_matrix"] * BATCH_PER_GPU
-    except Exception:
-        return None
+    this batch (profiles/r02_traffic.json), or None."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return t["dram_bytes_per_matrix"] * BATCH_PER_GPU
+        except Exception:
+            continue
+    return None
+
+
+
+def kernel_name(m, algo, n, mode):
+    cls = m.kernel_class(algo, n, mode)
+    if mode == "fast" and cls == "warp_smem" and 12 < n <= 32 and os.environ.get("MODCHOL_WIP", "1") != "0":
+        return f"{cls}: wip_kernel<{algo.upper()}, n={n}> (implicit pivoting, L in tensor memory, DMMA updates)"
+    names = {"warp_smem": "wsm_se_kernel / wsm_gmw_kernel", "cta_packed": "csm_*_kernel",
+             "cta_blocked": "bsm_gmw_kernel", "cta_smem": "*_cta_kernel", "cta_gmem": "*_cta_kernel",
+             "warp32": "warp_*_kernel"}
+    return f"{cls}: {names.get(cls, cls)}<{algo.upper()}, {mode}>"
+
+
+def time_steps(torch, fn, steps, warmup):
+    """Device time of `steps` calls of fn() on torch's current stream, in ms per call."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def other_configs(torch, np, m, dev, peak):
+    """Short timed runs of BASELINE.json configs[0..3] and of the reference's bench family
+    (rank 0, N = 1).  Inputs are resident; every batch is larger than the L2 or flushed by the
+    alternation of input and output streams (stated per entry)."""
+    import oracle
+    from modcholesky_b200 import utils
+    out = {}
+    dfma, dmma = m.fp64_peak_tflops()
+    out["fp64_peaks_tflops"] = {"dfma": dfma, "dmma_m8n8k4": dmma,
+                                "how": "modchol_fp64_peak_tflops: dependent FMA / mma.sync chains, CUDA events"}
+
+    def device_case(algo, n, batch, a, tag):
+        ent = {"workload": tag, "algo": algo, "n": n, "batch": batch,
+               "bytes_touched_per_step": batch * (16 * n * n + 16 * n)}
+        for mode in ("fast", "strict"):
+            ms = time_steps(torch, lambda: m.factor_batched(algo, a, mode=mode), 5, 3)
+            rate = batch / (ms * 1e-3)
+            gbs = rate * (16 * n * n + 16 * n) / 1e9
+            ent[mode] = {"matrices_per_sec": rate, "ms_per_step": ms, "kernel": kernel_name(m, algo, n, mode),
+                         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                      "frac": gbs / peak}}
+            if n >= 128:
+                tf = rate * n ** 3 / 3.0 / 1e12
+                ent[mode]["fp64"] = {"achieved_tflops": tf, "frac_of_dfma_peak": tf / dfma,
+                                     "frac_of_dmma_peak": tf / dmma, "flops_per_matrix": n ** 3 / 3.0}
+        return ent
+
+    # configs[1..3]: family F1 (symmetric uniform), as the headline
+    for key, algo, n, batch in (("configs[1]", "se99", 16, 1 << 20), ("configs[2]", "se90", 64, 200_000),
+                                ("configs[3]", "gmw81", 256, 4096)):
+        a = gen_batch(torch, batch, n, SEED + 17 * n, dev)
+        ent = device_case(algo, n, batch, a, f"{algo} n={n}, {batch} symmetric-uniform indefinite matrices, resident")
+        d = m.factor_batched(algo, a, mode="fast")
+        resid, flags = m.verify_batched(a, d)
+        amax = a.abs().amax(dim=(1, 2))
+        bar = torch.clamp(8.0 * 2.220446049250313e-16 * (amax + d.e.amax(dim=1)) / torch.clamp(amax, min=1.0), min=1e-12)
+        ent["verified_on_device"] = bool(int(flags.max()) == 0 and bool((resid <= bar).all()))
+        if key == "configs[1]":
+            vms = time_steps(torch, lambda: m.verify_batched(a, d), 3, 1)
+            ent["verify_ms"] = vms
+        out[key] = ent
+        del a, d, resid, flags
+        torch.cuda.empty_cache()
+
+    # the reference's bench family on its own shapes (benches/bench.rs:46-83): Q D Q^T with the
+    # bit-exact seeded factors, assembled on the device; the CPU column is the oracle on the
+    # same bytes (all host threads)
+    fam = {}
+    for n, batch, cpu_n in ((12, 1 << 18, 1 << 14), (128, 8192, 256), (256, 4096, 64)):
+        v, dg = utils.bench_input_batch(n, batch)
+        vd, dd = torch.from_numpy(v).to(dev), torch.from_numpy(dg).to(dev)
+        asm_ms = time_steps(torch, lambda: m.assemble_qdqt_batched(vd, dd), 2, 1)
+        a = m.assemble_qdqt_batched(vd, dd)
+        ent = {"batch": batch, "assemble_ms": asm_ms, "algos": {}}
+        ah = a[:cpu_n].cpu().numpy()
+        for algo in ("gmw81", "se90", "se99"):
+            c = device_case(algo, n, batch, a, f"bench.rs {algo}_{n}x{n}_nd family")
+            t0 = time.perf_counter()
+            ref = oracle.factor_batched(algo, ah, threads=0)
+            dt = time.perf_counter() - t0
+            ds = m.factor_batched(algo, a[:cpu_n], mode="strict")
+            same = bool(np.array_equal(ds.l.cpu().numpy(), ref.l) and np.array_equal(ds.e.cpu().numpy(), ref.e)
+                        and np.array_equal(ds.p.cpu().numpy().astype(np.uint64), ref.p))
+            ent["algos"][algo] = {"gpu_fast_matrices_per_sec": c["fast"]["matrices_per_sec"],
+                                  "gpu_strict_matrices_per_sec": c["strict"]["matrices_per_sec"],
+                                  "gpu_fast_roofline_frac": c["fast"]["roofline"]["frac"],
+                                  "kernel_fast": c["fast"]["kernel"],
+                                  "cpu_oracle_matrices_per_sec": cpu_n / dt, "cpu_threads": ref.threads,
+                                  "cpu_sample": cpu_n, "strict_bit_exact_vs_oracle": same}
+        fam[f"n={n}"] = ent
+        del a, vd, dd
+        torch.cuda.empty_cache()
+    out["reference_bench_family"] = fam
+
+    # configs[0]: the reference's single-matrix case -- one 10x10 / 12x12 Q D Q^T matrix through
+    # the three algorithms on the CPU (oracle, one thread, us per call) and the latency of the same
+    # call through the trait path on the GPU (batch = 1: HOST buffers, and DEVICE buffers)
+    c0 = {}
+    for n in (10, 12):
+        a1 = utils.bench_input_dense(n)
+        ent = {}
+        for algo in ("gmw81", "se90", "se99"):
+            reps = 2000
+            stack = np.ascontiguousarray(np.broadcast_to(a1, (reps, n, n)))
+            oracle.factor_batched(algo, stack[:16], threads=1)
+            t0 = time.perf_counter()
+            oracle.factor_batched(algo, stack, threads=1)
+            cpu_us = (time.perf_counter() - t0) / reps * 1e6
+            arr = m.Array2(a1, mode="strict")
+            fn = getattr(arr, "mod_cholesky_" + algo)
+            for _ in range(20):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                fn()
+            host_us = (time.perf_counter() - t0) / 200 * 1e6
+            ad = torch.from_numpy(a1[None]).to(dev)
+            for _ in range(20):
+                m.factor_batched(algo, ad)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                m.factor_batched(algo, ad)
+            torch.cuda.synchronize()
+            dev_us = (time.perf_counter() - t0) / 200 * 1e6
+            kern_us = time_steps(torch, lambda: m.factor_batched(algo, ad), 50, 5) * 1e3
+            ent[algo] = {"cpu_oracle_us_per_call": cpu_us, "gpu_trait_call_us_host_buffers": host_us,
+                         "gpu_call_us_device_buffers": dev_us, "gpu_device_time_us": kern_us}
+        c0[f"{n}x{n}"] = ent
+    c0["note"] = ("benches/bench.rs has 12x12 (bench.rs:46-57), BASELINE.json says 10x10: both; CPU = C oracle, "
+                  "one thread, 2000 calls; GPU = Array2(...).mod_cholesky_*() with numpy input (H2D + kernel + "
+                  "D2H per call) and the same call on resident torch tensors (wall clock incl. Python)")
+    out["configs[0]"] = c0
+    return out
 
 
 def cpu_baseline(a_host, threads=0):
@@ -176,6 +324,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":
@@ -287,9 +436,10 @@ def main():
     achieved = batch * ALG_BYTES / (ms_per_step * 1e-3) / 1e9      # per GPU: one launch per step
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(),
-                "kernel": f"{m.kernel_class(ALGO, N_MAT, args.mode)}: wsm_se_kernel<SE99, R=1, {args.mode}> (one launch per step)",
+                "kernel": kernel_name(m, ALGO, N_MAT, args.mode) + " (one launch per step)",
                 "algorithmic_bytes_per_matrix": ALG_BYTES, "peak_source": peak_src,
-                "note": "instruction-issue bound (shared-memory-resident, left-looking), not HBM bound: see profiles/r01_notes.md"}
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture (profiles/r02_traffic.json), scaled to this batch",
+                "note": "latency / issue bound (one warp per matrix, 32 dependent pivot steps), not HBM bound: see profiles/r02_notes.md"}
 
     line = {
         "metric": "matrices_per_sec", "value": value, "unit": "matrices/s", "n_gpus": world,
@@ -318,6 +468,10 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "matrices/s", "cores": cores, "kind": "port",
                                 "sample": f"{sub.shape[0]} of the {batch} matrices, {secs:.1f} s wall on "
                                           f"{cores} threads (C restatement of the reference; Rust absent)"}
+    if rank == 0 and world == 1 and not args.no_configs:
+        del a
+        torch.cuda.empty_cache()
+        line["configs"] = other_configs(torch, np, m, dev, peak)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -128,6 +128,20 @@ int modchol_factor_solve_batched_f64(int algo, int mode, int64_t batch, int32_t 
                                      double *e, uint64_t *p, int32_t *phase2_start, int mem_kind,
                                      void *stream);
 
+/* Device-side assembly of the reference's bench inputs (benches/bench.rs:48-53):
+ *   A_b = Q_b D_b Q_b^T,  Q_b = H_0 H_1 ... H_{nrefl-1},  H_r = I - 2 v_r v_r^T / (v_r^T v_r)
+ * (utils.rs:116-121 random_householder is H for one seeded v; utils.rs:126-147 random_diagonal
+ * is D).  v: batch x nrefl x n Householder vectors, d: batch x n diagonals, a: batch x n x n
+ * output, exactly symmetric.  Each reflector is applied as a symmetric rank-2 update
+ * (O(nrefl n^2) per matrix); the result equals the reference's dense products to rounding. */
+int modchol_assemble_qdqt_batched_f64(int64_t batch, int32_t n, int32_t nrefl, const double *v,
+                                      const double *d, double *a, int mem_kind, void *stream);
+
+/* Measured FP64 issue peaks of the current device in TFLOP/s: dependent fused-multiply-add
+ * chains on the FP64 pipe and m8n8k4 tensor-pipe operations (either pointer may be NULL).
+ * bench.py quotes the large-n kernels against them.  Synchronous, a few milliseconds. */
+int modchol_fp64_peak_tflops(double *dfma_tflops, double *dmma_tflops);
+
 /* Name of the kernel class the dispatcher uses for (algo, mode, n) -- e.g. "warp32",
  * "cta_smem", "cta_gmem" -- for logging and tests.  Never NULL. */
 const char *modchol_kernel_class(int algo, int mode, int32_t n);

@@ -9,7 +9,7 @@ from . import utils  # noqa: F401
 from ._lib import (  # noqa: F401
     GMW81, SE90, SE99, MEM_DEVICE, MEM_HOST, MODE_FAST, MODE_STRICT, ModCholError, lib)
 from .api import (  # noqa: F401
-    Array2, Array3, Decomposition, GershgorinCircles, ModCholeskyGMW81, ModCholeskySE90,
+    Array2, Array3, Decomposition, assemble_qdqt_batched, fp64_peak_tflops, GershgorinCircles, ModCholeskyGMW81, ModCholeskySE90,
     ModCholeskySE99, NotSquareError, factor, factor_batched, factor_solve_batched,
     gershgorin_circles_batched,
     mod_cholesky_gmw81, mod_cholesky_se90, mod_cholesky_se99, solve_batched, verify_batched)

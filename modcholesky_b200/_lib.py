@@ -27,6 +27,8 @@ EXPORTS = (
     "modchol_verify_batched_f64",
     "modchol_solve_batched_f64",
     "modchol_factor_solve_batched_f64",
+    "modchol_assemble_qdqt_batched_f64",
+    "modchol_fp64_peak_tflops",
     "modchol_kernel_class",
     "modchol_set_small_kernel_family",
     "modchol_launch_count",
@@ -74,6 +76,10 @@ def lib() -> ctypes.CDLL:
     L.modchol_factor_solve_batched_f64.argtypes = [ctypes.c_int, ctypes.c_int, i64, i32, i32, vp, vp, vp,
                                                    vp, vp, vp, vp, ctypes.c_int, vp]
     L.modchol_factor_solve_batched_f64.restype = ctypes.c_int
+    L.modchol_assemble_qdqt_batched_f64.argtypes = [i64, i32, i32, vp, vp, vp, ctypes.c_int, vp]
+    L.modchol_assemble_qdqt_batched_f64.restype = ctypes.c_int
+    L.modchol_fp64_peak_tflops.argtypes = [vp, vp]
+    L.modchol_fp64_peak_tflops.restype = ctypes.c_int
     L.modchol_kernel_class.argtypes = [ctypes.c_int, ctypes.c_int, i32]
     L.modchol_kernel_class.restype = ctypes.c_char_p
     L.modchol_set_small_kernel_family.argtypes = [ctypes.c_int]

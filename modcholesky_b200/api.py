@@ -285,6 +285,41 @@ def factor_solve_batched(algo, a, b, mode="strict", return_factors: bool = False
     return (x, d) if return_factors else x
 
 
+def assemble_qdqt_batched(v, d):
+    """The reference's bench inputs (benches/bench.rs:48-53) assembled on the GPU:
+    A_b = Q_b diag(d_b) Q_b^T with Q_b the product of the Householder reflectors of the vectors
+    v[b, 0], v[b, 1], ... (utils.rs:116-121).  `v`: (batch, nrefl, n), `d`: (batch, n); numpy
+    (host) or torch CUDA tensors (device).  Returns (batch, n, n), exactly symmetric."""
+    L = _lib.lib()
+    if v.ndim != 3 or d.ndim != 2 or v.shape[0] != d.shape[0] or v.shape[2] != d.shape[1]:
+        raise ValueError(f"expected v (batch, nrefl, n) and d (batch, n), got {tuple(v.shape)}, {tuple(d.shape)}")
+    b, m, n = v.shape
+    if _is_torch(d):
+        import torch
+        d = _dev_tensor(d, "d", torch.float64)
+        v = _dev_tensor(v, "v", torch.float64, (b, m, n), d.device)
+        with torch.cuda.device(d.device):
+            a = torch.empty((b, n, n), dtype=torch.float64, device=d.device)
+            st = torch.cuda.current_stream(d.device).cuda_stream
+            rc = L.modchol_assemble_qdqt_batched_f64(b, n, m, v.data_ptr(), d.data_ptr(), a.data_ptr(),
+                                                     _lib.MEM_DEVICE, ctypes.c_void_p(st))
+        _lib.check(rc)
+        return a
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    a = np.empty((b, n, n), dtype=np.float64)
+    _lib.check(L.modchol_assemble_qdqt_batched_f64(b, n, m, v.ctypes.data, d.ctypes.data, a.ctypes.data,
+                                                   _lib.MEM_HOST, None))
+    return a
+
+
+def fp64_peak_tflops():
+    """(DFMA, DMMA) issue peaks of the current device in TFLOP/s, measured by the library."""
+    x, y = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    _lib.check(_lib.lib().modchol_fp64_peak_tflops(ctypes.byref(x), ctypes.byref(y)))
+    return float(x.value), float(y.value)
+
+
 # ---- the reference's trait spelling -----------------------------------------------------
 class ModCholeskyGMW81:
     """gmw81.rs:24-32: the default body panics with "Not implemented!"."""

@@ -502,6 +502,26 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
     return MODCHOL_OK;
 }
 
+// n <= 64: one warp per matrix, L L^T on the FP64 tensor pipe; larger n: one CTA per matrix
+void launch_verify(long long batch, int n, const double* a, const double* l, const double* e,
+                   const unsigned long long* p, double* resid, int* flags, int sms, cudaStream_t st)
+{
+    if (n <= 64) {
+        const unsigned grid = (unsigned)std::min<long long>((batch + 3) / 4, (long long)sms * 16);
+        if (n <= 16)
+            verify_warp_kernel<2><<<grid, 128, 0, st>>>(batch, n, a, l, e, p, resid, flags);
+        else if (n <= 32)
+            verify_warp_kernel<4><<<grid, 128, 0, st>>>(batch, n, a, l, e, p, resid, flags);
+        else if (n <= 48)
+            verify_warp_kernel<6><<<grid, 128, 0, st>>>(batch, n, a, l, e, p, resid, flags);
+        else
+            verify_warp_kernel<8><<<grid, 128, 0, st>>>(batch, n, a, l, e, p, resid, flags);
+        return;
+    }
+    const unsigned grid = (unsigned)std::min<long long>(batch, (long long)sms * 8);
+    verify_kernel<<<grid, 256, 0, st>>>(batch, n, a, l, e, p, resid, flags);
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -696,10 +716,9 @@ int modchol_verify_batched_f64(int64_t batch, int32_t n, const double* a, const 
     int rc = ctx_init(dev);
     if (rc)
         return rc;
-    const unsigned grid = (unsigned)std::min<long long>(batch, (long long)g_ctx[dev].sms * 8);
     auto pu = reinterpret_cast<const unsigned long long*>(p);
     if (mem_kind == MODCHOL_MEM_DEVICE) {
-        verify_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(batch, n, a, l, e, pu, resid, flags);
+        launch_verify(batch, n, a, l, e, pu, resid, flags, g_ctx[dev].sms, static_cast<cudaStream_t>(stream));
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
         return MODCHOL_OK;
@@ -721,7 +740,7 @@ int modchol_verify_batched_f64(int64_t batch, int32_t n, const double* a, const 
     if (ce == cudaSuccess) ce = cudaMemcpy(de, e, (size_t)batch * n * 8, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = cudaMemcpy(dp, p, (size_t)batch * n * 8, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) {
-        verify_kernel<<<grid, 256>>>(batch, n, da, dl, de, dp, dr, df);
+        launch_verify(batch, n, da, dl, de, dp, dr, df, g_ctx[dev].sms, nullptr);
         g_launches.fetch_add(1);
         ce = cudaGetLastError();
     }
@@ -849,6 +868,104 @@ int modchol_factor_solve_batched_f64(int algo, int mode, int64_t batch, int32_t 
         return rc;
     if (ce != cudaSuccess)
         return fail(MODCHOL_ERR_CUDA, "factor_solve: %s", cudaGetErrorString(ce));
+    return MODCHOL_OK;
+}
+
+int modchol_assemble_qdqt_batched_f64(int64_t batch, int32_t n, int32_t nrefl, const double* v,
+                                      const double* d, double* a, int mem_kind, void* stream)
+{
+    g_err.clear();
+    if (batch < 0 || n < 1 || nrefl < 0 || (batch > 0 && (!d || !a || (nrefl > 0 && !v))))
+        return fail(MODCHOL_ERR_BAD_ARG, "bad argument");
+    if (n > MODCHOL_MAX_N)
+        return fail(MODCHOL_ERR_UNSUPPORTED, "n too large");
+    if (mem_kind != MODCHOL_MEM_HOST && mem_kind != MODCHOL_MEM_DEVICE)
+        return fail(MODCHOL_ERR_BAD_ARG, "unknown mem_kind %d", mem_kind);
+    if (device_count() < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (batch == 0)
+        return MODCHOL_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    const size_t smem = (size_t)(3 * n + 66) * sizeof(double);   // <= 48.5 KB at n = 2048
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] {
+        cudaFuncSetAttribute(assemble_qdqt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)((3 * MODCHOL_MAX_N + 66) * sizeof(double)));
+    });
+    const unsigned grid = (unsigned)std::min<long long>(batch, (long long)g_ctx[dev].sms * 8);
+    if (mem_kind == MODCHOL_MEM_DEVICE) {
+        assemble_qdqt_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(batch, n, nrefl, v, d, a);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+        return MODCHOL_OK;
+    }
+    const size_t nn = (size_t)n * n;
+    double *dv = nullptr, *ddg = nullptr, *da = nullptr;
+    cudaError_t ce = cudaMalloc(&da, batch * nn * 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&ddg, (size_t)batch * n * 8);
+    if (ce == cudaSuccess && nrefl > 0) ce = cudaMalloc(&dv, (size_t)batch * nrefl * n * 8);
+    if (ce == cudaSuccess) ce = cudaMemcpy(ddg, d, (size_t)batch * n * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && nrefl > 0) ce = cudaMemcpy(dv, v, (size_t)batch * nrefl * n * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        assemble_qdqt_kernel<<<grid, 256, smem>>>(batch, n, nrefl, dv, ddg, da);
+        g_launches.fetch_add(1);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(a, da, batch * nn * 8, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(ddg); cudaFree(dv);
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "assemble_qdqt: %s", cudaGetErrorString(ce));
+    return MODCHOL_OK;
+}
+
+int modchol_fp64_peak_tflops(double* dfma_tflops, double* dmma_tflops)
+{
+    g_err.clear();
+    if (device_count() < 1)
+        return fail(MODCHOL_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = ctx_init(dev);
+    if (rc)
+        return rc;
+    const int sms = g_ctx[dev].sms, iters = 1 << 14, threads = 512, blocks = sms * 4;
+    double* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best[2] = {0.0, 0.0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 4; ++rep) {   // rep 0 warms up
+            cudaEventRecord(e0);
+            if (which == 0)
+                fp64_dfma_probe_kernel<<<blocks, threads>>>(iters, 0.999999, sink);
+            else
+                fp64_dmma_probe_kernel<<<blocks, threads>>>(iters, 0.999999, sink);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            g_launches.fetch_add(1);
+            // DFMA: 8 per thread and iteration, 2 flops each; DMMA: 4 per warp, 8x8x4x2 flops each
+            const double flops = which == 0 ? (double)blocks * threads * iters * 8.0 * 2.0
+                                            : (double)blocks * (threads / 32) * iters * 4.0 * 512.0;
+            if (rep > 0 && ms > 0.f)
+                best[which] = std::max(best[which], flops / (ms * 1e-3) / 1e12);
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaError_t ce = cudaGetLastError();
+    cudaFree(sink);
+    if (ce != cudaSuccess)
+        return fail(MODCHOL_ERR_CUDA, "fp64 probe: %s", cudaGetErrorString(ce));
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
     return MODCHOL_OK;
 }
 

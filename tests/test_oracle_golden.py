@@ -137,3 +137,25 @@ def test_batched_threads_agree(oracle):
     r1 = oracle.factor_batched("se99", a, threads=1)
     r4 = oracle.factor_batched("se99", a, threads=4)
     assert np.array_equal(r1.l, r4.l) and np.array_equal(r1.e, r4.e) and np.array_equal(r1.p, r4.p)
+
+
+def test_vectorised_generator_tables_equal_the_scalar_restatement():
+    """The per-seed tables used to build batches of the reference's bench family are the same
+    bits as the scalar XorShift / Uniform restatement (utils.rs:116-147)."""
+    from modcholesky_b200 import utils
+    hv, dg = utils.householder_vector_table(12), utils.diagonal_table(12)
+    for s in (0, 2, 9, 23, 90, 255):
+        assert np.array_equal(hv[s], utils.householder_vector(12, s))
+        assert np.array_equal(dg[s], np.diag(utils.random_diagonal(12, (-1.0, 1000.0), 1, s)))
+    dg3 = utils.diagonal_table(10, (-2.0, 5.0), 3)
+    for s in (1, 77):
+        assert np.array_equal(dg3[s], np.diag(utils.random_diagonal(10, (-2.0, 5.0), 3, s)))
+    v, d = utils.bench_input_batch(12, 4)
+    v0, d0 = utils.bench_input_factors(12)
+    assert np.array_equal(v[0], v0) and np.array_equal(d[0], d0)
+    m = np.diag(d0)
+    for r in (2, 1, 0):
+        h = np.eye(12) - 2.0 / np.dot(v0[r], v0[r]) * np.outer(v0[r], v0[r])
+        m = h @ m @ h
+    dense = utils.bench_input_dense(12)
+    assert np.abs(m - dense).max() <= 1e-13 * np.abs(dense).max()

@@ -50,7 +50,7 @@ def _assert_bit_exact(tag, got, ref):
 RELAXED = {"checked": 0, "e_relaxed": 0, "recon_relaxed": 0}   # printed by the last test of this file
 
 
-def _assert_tolerance(tag, a, got, ref, algo=None):
+def _assert_tolerance(tag, a, got, ref, algo=None, min_firm=0.9):
     """FAST-mode bars.  The plain north-star bars (E to 1e-10 of ||E||, reconstruction to 1e-12 of
     ||A||) are asserted for every matrix except the two GMW81 situations in which they are below
     the f64 resolution of the quantities themselves; those matrices are counted in RELAXED."""
@@ -62,7 +62,7 @@ def _assert_tolerance(tag, a, got, ref, algo=None):
     firm = ok & (ref.margin > TIE_MARGIN)
     same_p = (p == ref.p).all(axis=1)
     assert same_p[firm].all(), f"{tag}: p differs on {(~same_p[firm]).sum()} non-tie matrices"
-    assert firm.sum() >= 0.9 * ok.sum(), f"{tag}: too many rounding ties to be meaningful"
+    assert firm.sum() >= min_firm * ok.sum(), f"{tag}: too many rounding ties to be meaningful"
     cmp = firm & same_p
     escale = np.maximum(np.abs(ref.e).max(axis=1), 1e-300)
     anorm = np.maximum(np.abs(a).max(axis=(1, 2)), 1.0)
@@ -540,6 +540,79 @@ def test_torch_arguments_are_checked(torch_cuda):
         m.factor_solve_batched("se99", a, rhs[:4])
     x = m.solve_batched(d, rhs)          # and the well-formed call still works
     assert x.shape == rhs.shape
+
+
+@pytest.mark.parametrize("n", [1, 5, 16, 17, 32, 33, 48, 49, 64, 65, 100])
+def test_verifier_matches_numpy_and_raises_every_flag(oracle, torch_cuda, n):
+    """The on-device acceptance check (warp-per-matrix DMMA kernel for n <= 64, CTA kernel above)
+    against numpy's evaluation of the same identity (se99.rs:221-231), and each flag bit."""
+    torch = torch_cuda
+    b = 24
+    a = matgen.make("uniform", 900 + n, b, n)
+    ref = oracle.factor_batched("se99", a)
+    l, e, p = ref.l.copy(), ref.e.copy(), ref.p.copy()
+    want = np.array([identity_residual(a[i], l[i], e[i], p[i]) for i in range(b)])
+    want = want / np.maximum(1.0, np.abs(a).max(axis=(1, 2)))
+    d = m.Decomposition(torch.from_numpy(l).cuda(), torch.from_numpy(e).cuda(),
+                        torch.from_numpy(p.astype(np.int64)).cuda())
+    resid, flags = m.verify_batched(torch.from_numpy(a).cuda(), d)
+    assert int(flags.max()) == 0
+    assert np.abs(resid.cpu().numpy() - want).max() <= 1e-14, n
+    rh, fh = m.verify_batched(a, m.Decomposition(l, e, p))          # HOST buffers
+    assert np.array_equal(rh, resid.cpu().numpy()) and int(fh.max()) == 0
+    if n < 2:
+        return
+    # matrix 0: p not a permutation; 1: e < 0; 2: dirty strict upper triangle; 3: NaN in L;
+    # 4: one wrong entry of L (no flag, residual large); 5: out-of-range index
+    p[0, 0] = p[0, 1]
+    e[1, n - 1] = -1.0
+    l[2, 0, n - 1] = 0.5
+    l[3, n - 1, 0] = np.nan
+    l[4, n - 1, 0] += 1.0
+    p[5, n - 1] = n + 3
+    d = m.Decomposition(torch.from_numpy(l).cuda(), torch.from_numpy(e).cuda(),
+                        torch.from_numpy(p.astype(np.int64)).cuda())
+    resid, flags = m.verify_batched(torch.from_numpy(a).cuda(), d)
+    resid, flags = resid.cpu().numpy(), flags.cpu().numpy()
+    assert flags[0] & 1 and np.isinf(resid[0])
+    assert flags[1] & 2
+    assert flags[2] & 4
+    assert flags[3] & 8 and not resid[3] <= 1e-12
+    assert flags[4] == 0 and resid[4] > 1e-3
+    assert flags[5] & 1 and np.isinf(resid[5])
+    assert (flags[6:] == 0).all() and (resid[6:] <= 1e-12).all()
+
+
+@pytest.mark.parametrize("n", [10, 12, 128, 256])
+def test_device_assembly_of_the_reference_bench_inputs(oracle, torch_cuda, n):
+    """benches/bench.rs:48-53: A = Q D Q^T from the bit-exact seeded factors, assembled on the GPU
+    (rank-2 reflector updates) against the reference's dense construction in numpy; then the
+    factorisations of the SAME device-built bytes against the oracle (f2)."""
+    torch = torch_cuda
+    from modcholesky_b200 import utils
+    v1, d1 = utils.bench_input_factors(n)
+    dense = utils.bench_input_dense(n)
+    b = 32 if n <= 128 else 8
+    v, dg = utils.bench_input_batch(n, b)
+    assert np.array_equal(v[0], v1) and np.array_equal(dg[0], d1)
+    a = m.assemble_qdqt_batched(torch.from_numpy(v).cuda(), torch.from_numpy(dg).cuda()).cpu().numpy()
+    assert np.array_equal(a, np.transpose(a, (0, 2, 1))), "assembled matrices must be exactly symmetric"
+    assert np.abs(a[0] - dense).max() <= 1e-13 * np.abs(dense).max()
+    ah = m.assemble_qdqt_batched(v, dg)                                # HOST buffers
+    assert np.array_equal(ah, a)
+    w = np.linalg.eigvalsh(a[0])
+    assert np.allclose(np.sort(w), np.sort(d1), rtol=1e-9, atol=1e-9 * np.abs(d1).max())
+    for algo in ALGOS:
+        ref = oracle.factor_batched(algo, a)
+        _assert_bit_exact(f"{algo} bench-input n={n} strict", _gpu(torch, algo, a, "strict"), ref)
+        # (Q D Q^T with three reflectors is D plus a rank-6 term: 20-30 % of these matrices have a
+        # pivot decision closer than 1e-9 -- rounding ties, which FAST may resolve either way)
+        _assert_tolerance(f"{algo} bench-input n={n} fast", a, _gpu(torch, algo, a, "fast"), ref, min_firm=0.4)
+
+
+def test_fp64_peak_probe(torch_cuda):
+    dfma, dmma = m.fp64_peak_tflops()
+    assert 10.0 < dfma < 80.0 and 10.0 < dmma < 80.0, (dfma, dmma)
 
 
 def test_zz_report_relaxed_bar_counts():

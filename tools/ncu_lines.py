@@ -37,10 +37,15 @@ print(f"total warp-instr {tot}, per matrix {tot / batch:.0f}")
 print(f"{'instr/matrix':>12s} {'%':>5s} {'stall%':>6s}  location")
 for ex, st, f, ln, src in sorted(rows, reverse=True)[:top]:
     print(f"{ex / batch:12.1f} {100 * ex / tot:5.1f} {100 * st / max(stt, 1):6.1f}  {f}:{ln}  {src[:90]}")
+if os.environ.get("BY_STALL"):
+    print("by stall samples:")
+    for ex, st, f, ln, src in sorted(rows, key=lambda r: -r[1])[:top]:
+        print(f"{ex / batch:12.1f} {100 * ex / tot:5.1f} {100 * st / max(stt, 1):6.1f}  {f}:{ln}  {src[:90]}")
 if len(sys.argv) > 4:   # region sums: file:lo-hi,...
     print("regions:")
     for spec in sys.argv[4].split(","):
         f, rng = spec.split(":")
         lo, hi = map(int, rng.split("-"))
         ex = sum(r[0] for r in rows if r[2] == f and lo <= r[3] <= hi)
-        print(f"  {spec:28s} {ex / batch:9.1f}  {100 * ex / tot:5.1f}%")
+        stx = sum(r[1] for r in rows if r[2] == f and lo <= r[3] <= hi)
+        print(f"  {spec:28s} {ex / batch:9.1f}  {100 * ex / tot:5.1f}%  stall {100 * stx / max(stt, 1):5.1f}%")
