@@ -21,6 +21,8 @@ NVCC_FLAGS = [
 
 # (source, object name, extra defines)
 UNITS = [("modchol_api.cu", "api.o", []), ("bsm_inst.cu", "bsm.o", [])] + [
+    ("lwm_inst.cu", f"lwm_a{a}.o", [f"-DMODCHOL_INST_ALGO={a}"]) for a in (0, 1, 2)
+] + [
     ("warp_inst.cu", f"warp_a{a}_s{s}.o", [f"-DMODCHOL_INST_ALGO={a}", f"-DMODCHOL_INST_STRICT={s}"])
     for a in (0, 1, 2) for s in (1, 0)
 ] + [

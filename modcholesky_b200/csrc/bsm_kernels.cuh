@@ -467,4 +467,319 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
     }
 }
 
+
+// SE90 / SE99 (se90.rs:38-181, se99.rs:35-201) in the same blocked form: thread = permuted position,
+// running diagonal and Gershgorin bound in registers, FAST arithmetic of wip_kernels.cuh.  A phase
+// switch ends the current panel early (its columns are written out and applied to the trailing
+// block), so that the Gershgorin pass (se90.rs:105-110, se99.rs:125-130) reads the trailing
+// block as the reference holds it; later panels start at the switch column.
+template <int kAlgo, int kThreads, int KB, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+bsm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __restrict__ L,
+              double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nwarps = kThreads >> 5;
+    const int ldp = bsm_ldp(n);
+    const int npad = (n + 7) & ~7;
+    const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
+    const unsigned pb = smb;                                        // panel: column c at pb + 8 c ldp
+    const unsigned tdb = pb + 8u * (unsigned)(KB * ldp);            // diagonal of T (trailing-update bookkeeping)
+    const unsigned lineb = tdb + 8u * (unsigned)npad;
+    BsmScratch sc;
+    sc.base = lineb + 8u * (unsigned)npad;
+    sc.buf = 0;
+    const unsigned scalb = sc.base + 4u * 192u + 8u * 64u;          // 8 doubles of scalars
+    const size_t nn = (size_t)n * n;
+    const int row = tid;
+    const bool rv = row < n;
+    const bool wide = (n & 1) == 0 && (((size_t)L) & 15) == 0;
+
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const double* Ab = A + (size_t)b * nn;
+        double* Lb = L + (size_t)b * nn;
+        // ---- in: the strict upper triangle of A is T transposed; diagonal to registers -----------
+        for (int k = tid >> 5; k < n; k += nwarps)
+            for (int i = k + 1 + lane; i < n; i += 32)
+                Lb[(size_t)k * n + i] = __ldg(Ab + (size_t)k * n + i);
+        double cd = rv ? __ldg(Ab + (size_t)row * (n + 1)) : 0.0;   // running diagonal
+        if (row < npad)
+            sts_f64(tdb + 8u * (unsigned)row, cd);
+        double ev = 0.0, g = 0.0;
+        int perm = row;
+        // gamma = max |a_ii| folded from 0.0 (se90.rs:55-57, se99.rs:54-56)
+        const double gamma = bsm_extreme<true>(sc, nwarps, fabs(cd), rv, 0.0);
+        const double taugamma = dmul(MODCHOL_TAU, gamma);
+        __syncthreads();   // T is in place (block-scope visibility of the global stores)
+
+        int j = 0, j0 = 0, c = 0, kstart = -1, st = 0;
+        double delta_prev = 0.0, dmin_carry = 0.0;
+        bool have_dmin = false;
+
+        // symmetric exchange j <-> m (utils.rs:30-49), global side, fused with the read of column j,
+        // then minus the pending panel columns; the shared-memory side follows the step's reduction
+        // barrier (finish_exchange), see bsm_gmw_kernel
+        auto exchange_and_column = [&](int m) -> double {
+            const bool swp = m != j;
+            const int pj = m;
+            const int prow = (swp && row == j) ? m : ((swp && row == m) ? j : row);
+            double col = 0.0, x = 0.0, y = 0.0, lx = 0.0, ly = 0.0;
+            double *a1 = nullptr, *a2 = nullptr;
+            const bool tsw = swp && rv && row > j && row != m;
+            const bool lsw = swp && tid < j0;
+            if (tsw) {
+                a1 = Lb + (size_t)j * n + row;
+                a2 = row < m ? Lb + (size_t)row * n + m : Lb + (size_t)m * n + row;
+                x = *a1;
+                y = *a2;
+                col = y;
+            } else if (rv && row > j) {
+                col = Lb[(size_t)j * n + row];
+            }
+            if (lsw) {
+                lx = Lb[(size_t)j * n + tid];
+                ly = Lb[(size_t)m * n + tid];
+            }
+            if (swp && (row == j || row == m)) {                // scalars through shared memory
+                const unsigned q = scalb + (row == j ? 0u : 24u);
+                sts_f64(q, cd);
+                sts_f64(q + 8, (double)perm);
+                sts_f64(q + 16, g);
+            }
+            if (rv && row > j) {
+                const double* pr = sm + prow;
+                const double* pq = sm + pj;
+                double s0 = 0.0, s1 = 0.0;
+                int t = 0;
+                for (; t + 4 <= c; t += 4) {
+                    const double r0 = pr[(t + 0) * ldp], r1 = pr[(t + 1) * ldp];
+                    const double r2 = pr[(t + 2) * ldp], r3 = pr[(t + 3) * ldp];
+                    const double q0 = pq[(t + 0) * ldp], q1 = pq[(t + 1) * ldp];
+                    const double q2 = pq[(t + 2) * ldp], q3 = pq[(t + 3) * ldp];
+                    s0 = __fma_rn(r0, q0, s0);
+                    s1 = __fma_rn(r1, q1, s1);
+                    s0 = __fma_rn(r2, q2, s0);
+                    s1 = __fma_rn(r3, q3, s1);
+                }
+                for (; t < c; ++t)
+                    s0 = __fma_rn(pr[t * ldp], pq[t * ldp], s0);
+                col = dsub(col, dadd(s0, s1));
+            }
+            if (tsw) {
+                *a1 = y;
+                *a2 = x;
+            }
+            if (lsw) {
+                Lb[(size_t)j * n + tid] = ly;
+                Lb[(size_t)m * n + tid] = lx;
+            }
+            return col;
+        };
+        auto finish_exchange = [&](int m) {
+            if (m == j)
+                return;
+            if (row == j || row == m) {
+                const unsigned q = scalb + (row == j ? 24u : 0u);
+                cd = lds_f64(q);
+                perm = (int)lds_f64(q + 8);
+                g = lds_f64(q + 16);
+            }
+            if (tid < c) {
+                const unsigned q = pb + 8u * (unsigned)(tid * ldp);
+                const double u = lds_f64(q + 8u * j), w = lds_f64(q + 8u * m);
+                sts_f64(q + 8u * j, w);
+                sts_f64(q + 8u * m, u);
+            }
+        };
+        auto clear_panel = [&]() {
+            for (int q = tid; q < KB * ldp; q += kThreads)
+                sts_f64(pb + 8u * (unsigned)q, 0.0);
+            __syncthreads();
+            j0 = j;
+            c = 0;
+        };
+        // the panel's columns of L go to their final place; T -= P P^T on the trailing block
+        auto flush = [&]() {
+            __syncthreads();
+            if (c > 0) {
+                if (rv && row >= j0) {
+                    const int cnt = min(c, row - j0 + 1);
+                    double* dst = Lb + (size_t)row * n + j0;
+                    for (int t = 0; t < cnt; ++t)
+                        dst[t] = lds_f64(pb + 8u * (unsigned)(t * ldp + row));
+                }
+                if (j < n)
+                    bsm_trailing_update<KB>(Lb, n, j, pb, ldp, tdb, wide);
+            }
+            __syncthreads();
+        };
+
+        // ---- phase 1 (se90.rs:61-96, se99.rs:61-109) ----------------------------------------------
+        while (st == 0) {
+            clear_panel();
+            while (c < KB) {
+                if (j == n) {
+                    st = 2;
+                    break;
+                }
+                double piv;
+                if (row == j)
+                    sts_f64(scalb + 56u, cd);   // diagonal at position j: row m takes it over below
+                const int m = bsm_argmax_first(sc, nwarps, cd, rv && row >= j, row, j, piv);
+                if (kAlgo == kSE99) {   // se99.rs:62-73, before the pivot is applied
+                    const double dmin = have_dmin ? dmin_carry
+                                                  : bsm_extreme<false>(sc, nwarps, cd, rv && row >= j, INFINITY);
+                    if (piv < taugamma || dmin < dmul(-MODCHOL_MU, piv)) {
+                        kstart = j;
+                        st = 1;
+                        break;
+                    }
+                }
+                const double col = exchange_and_column(m);
+                const bool live = rv && row > j;
+                const bool fast = fast_range_ok(piv);
+                const double y = rsqrt_normal(piv);
+                double sq = dmul(piv, y);
+                double cs = dmul(col, y);
+                // the scalars of positions j and m trade places after the reduction barrier
+                // (finish_exchange); row m already works with the diagonal it is about to receive
+                const double cdo = (m != j && row == m) ? lds_f64(scalb + 56u) : cd;
+                double dgn = __fma_rn(-cs, cs, cdo);
+                double nv = dgn;   // look-ahead value (se90.rs:70-77, se99.rs:82-89); FAST: the updated diagonal
+                if (!fast)
+                    wip_slow_p1(piv, col, cdo, sq, cs, dgn, nv);
+                const double la = bsm_extreme<false>(sc, nwarps, nv, live, INFINITY);
+                finish_exchange(m);
+                have_dmin = fast;
+                dmin_carry = la;
+                const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
+                if (la < thresh) {   // the pivot at j stays applied (se99.rs:90-93)
+                    kstart = j;
+                    st = 1;
+                    break;
+                }
+                if (live)
+                    cd = dgn;
+                if (rv && row >= j)
+                    sts_f64(pb + 8u * (unsigned)(c * ldp + row), row == j ? sq : cs);
+                ++j;
+                ++c;
+            }
+            flush();
+        }
+
+        if (st == 1 && kAlgo == kSE99 && kstart == n - 1) {   // se99.rs:115-119
+            if (row == n - 1) {
+                const double ej = tail1x1_e(cd, gamma);
+                ev = ej;
+                Lb[(size_t)(n - 1) * n + (n - 1)] = dsqrt(dadd(cd, ej));
+            }
+        } else if (st == 1) {
+            // ---- phase 2 (se90.rs:101-167, se99.rs:121-187) ----------------------------------------
+            // Gershgorin bounds of the trailing block (the pending columns were applied by flush()):
+            // g_i = a_ii - sum_{k >= j, k != i} |a_ik|, T(i,k) at l[k n + i] for i > k
+            if (rv && row >= j) {
+                double s0 = 0.0, s1 = 0.0;
+                int k = j;
+                for (; k + 2 <= row; k += 2) {
+                    s0 = dadd(s0, fabs(Lb[(size_t)k * n + row]));
+                    s1 = dadd(s1, fabs(Lb[(size_t)(k + 1) * n + row]));
+                }
+                for (; k < row; ++k)
+                    s0 = dadd(s0, fabs(Lb[(size_t)k * n + row]));
+                const double* rp = Lb + (size_t)row * n;
+                int i = row + 1;
+                for (; i + 2 <= n; i += 2) {
+                    s0 = dadd(s0, fabs(rp[i]));
+                    s1 = dadd(s1, fabs(rp[i + 1]));
+                }
+                for (; i < n; ++i)
+                    s0 = dadd(s0, fabs(rp[i]));
+                g = dsub(cd, dadd(s0, s1));
+            }
+            while (j + 2 < n) {
+                clear_panel();
+                while (c < KB && j + 2 < n) {
+                    double best;
+                    const int m = bsm_argmax_first(sc, nwarps, g, rv && row >= j, row, j, best);   // se90.rs:115
+                    if (row == m)
+                        sts_f64(scalb + 48u, cd);   // the pivot's diagonal, read after the next barrier
+                    const double col = exchange_and_column(m);
+                    const bool live = rv && row > j;
+                    const double acol = live ? abs_bits(col) : 0.0;
+                    const double normj = bsm_sum(sc, nwarps, acol);   // se90.rs:124, se99.rs:144
+                    double piv = lds_f64(scalb + 48u);
+                    finish_exchange(m);
+                    // E_jj (se90.rs:124-131, se99.rs:144-151)
+                    const double ej = max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
+                    piv = dadd(piv, ej);
+                    delta_prev = ej;
+                    // bound update (se90.rs:134-139, se99.rs:154-159) and column scaling
+                    const bool upd = fabs(dsub(piv, normj)) > MODCHOL_EPS;
+                    const double y = rsqrt_normal(piv);
+                    double sq = dmul(piv, y);
+                    double t = __fma_rn(-normj, dmul(y, y), 1.0);
+                    double cs = dmul(col, y);
+                    if (!fast_range_ok(piv))
+                        wip_slow_p2(piv, normj, col, sq, t, cs);
+                    if (live) {
+                        cd = __fma_rn(-cs, cs, cd);
+                        if (upd)
+                            g = __fma_rn(acol, t, g);
+                    }
+                    if (row == j)
+                        ev = ej;
+                    if (rv && row >= j)
+                        sts_f64(pb + 8u * (unsigned)(c * ldp + row), row == j ? sq : cs);
+                    ++j;
+                    ++c;
+                }
+                flush();
+            }
+            // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186); the trailing block is
+            // up to date
+            if (row == n - 2)
+                sts_f64(scalb + 48u, cd);
+            if (row == n - 1)
+                sts_f64(scalb + 56u, cd);
+            __syncthreads();
+            if (row == n - 2 || row == n - 1) {
+                double a00 = lds_f64(scalb + 48u), a11 = lds_f64(scalb + 56u);
+                double a10 = Lb[(size_t)(n - 2) * n + (n - 1)];
+                double lhi, llo;
+                eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);   // lower storage: m[0,1] == m[1,0]
+                const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
+                if (en > 0.0) {
+                    a00 = dadd(a00, en);
+                    a11 = dadd(a11, en);
+                }
+                a00 = dsqrt(a00);
+                a10 = ddiv(a10, a00);
+                a11 = dsqrt(dsub(a11, dmul(a10, a10)));
+                ev = en;
+                if (row == n - 2) {
+                    Lb[(size_t)(n - 2) * n + (n - 2)] = a00;
+                } else {
+                    Lb[(size_t)(n - 1) * n + (n - 2)] = a10;
+                    Lb[(size_t)(n - 1) * n + (n - 1)] = a11;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- out: strict upper triangle zero (se99.rs:189-192), e un-permuted (se99.rs:194-198), p
+        for (int k = tid >> 5; k < n; k += nwarps)
+            for (int i = k + 1 + lane; i < n; i += 32)
+                Lb[(size_t)k * n + i] = 0.0;
+        if (rv) {
+            E[(size_t)b * n + perm] = ev;
+            P[(size_t)b * n + row] = (unsigned long long)perm;
+        }
+        if (K && tid == 0)
+            K[b] = kstart;
+        __syncthreads();
+    }
+}
+
 }  // namespace modchol

@@ -204,7 +204,7 @@ int slot_reserve(Slot& s, size_t mats, int n)
 }
 
 // ---- size-class dispatch ---------------------------------------------------------------
-enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3, kClsCtaPacked = 4, kClsCtaBlocked = 5 };
+enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3, kClsCtaPacked = 4, kClsCtaBlocked = 5, kClsWarpPanel = 6 };
 
 // Which small-n family serves n <= 32 (0 auto, 1 registers, 2 shared memory); initialised
 // from MODCHOL_SMALL_KERNEL=reg|wsm, changed by modchol_set_small_kernel_family().
@@ -232,6 +232,15 @@ int bsm_min_n()
     return v;
 }
 
+// The warp-per-matrix panel kernels (lwm_kernels.cuh, 64 < n <= 256) are opt-in: measured behind
+// the block-level kernels at every size.  MODCHOL_LWM_MIN = smallest n they
+// serve, read per call so that tests and benchmarks can switch them on.
+int lwm_min_n()
+{
+    const char* e = getenv("MODCHOL_LWM_MIN");
+    return e ? atoi(e) : 100000;
+}
+
 KernelClass classify(int algo, int mode, int n, int smem_optin)
 {
     const bool reg_ok = warp_kernel_available(algo, mode, n);
@@ -246,6 +255,8 @@ KernelClass classify(int algo, int mode, int n, int smem_optin)
         return kClsWarpSmem;
     if (reg_ok)
         return kClsWarp;
+    if (lwm_kernel_available(algo, mode, n) && n >= lwm_min_n())
+        return kClsWarpPanel;
     if (bsm_kernel_available(algo, mode, n) && n >= bsm_min_n())
         return kClsCtaBlocked;
     if (csm_kernel_available(algo, mode, n))
@@ -305,6 +316,13 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
         g_launches.fetch_add(1);
         if (ce != cudaSuccess)
             return fail(MODCHOL_ERR_CUDA, "wsm kernel launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    if (cls == kClsWarpPanel) {
+        cudaError_t ce = launch_lwm_kernel(algo, n, batch, a, l, e, p, k, c.sms, st);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "lwm kernel launch failed: %s", cudaGetErrorString(ce));
         return MODCHOL_OK;
     }
     if (cls == kClsCtaBlocked) {
@@ -551,6 +569,7 @@ const char* modchol_kernel_class(int algo, int mode, int32_t n)
     case kClsWarpSmem: return "warp_smem";
     case kClsCtaPacked: return "cta_packed";
     case kClsCtaBlocked: return "cta_blocked";
+    case kClsWarpPanel: return "warp_panel";
     case kClsCtaSmem: return "cta_smem";
     default: return "cta_gmem";
     }

@@ -112,7 +112,29 @@ cudaError_t launch_bsm_kernel(int algo, int n, long long batch, const double* a,
                               unsigned long long* p, int* k, int sms, cudaStream_t st);
 inline bool bsm_kernel_available(int algo, int mode, int n)
 {
-    return mode == 1 && algo == 0 && n > 128 && n <= kBsmMaxN;
+    return mode == 1 && algo >= 0 && algo <= 2 && n > 128 && n <= kBsmMaxN;
+}
+
+// warp-per-matrix large-n kernels (lwm_kernels.cuh), FAST mode, 64 < n <= 256; defined in lwm_inst.cu
+constexpr int kLwmMaxN = 256;
+#define MODCHOL_DECL_LWM(a)                                                                             \
+    cudaError_t launch_lwm_a##a(int n, long long batch, const double* a_, double* l, double* e,        \
+                                unsigned long long* p, int* k, int sms, cudaStream_t st);
+MODCHOL_DECL_LWM(0)
+MODCHOL_DECL_LWM(1)
+MODCHOL_DECL_LWM(2)
+#undef MODCHOL_DECL_LWM
+inline bool lwm_kernel_available(int algo, int mode, int n)
+{
+    return mode == 1 && algo >= 0 && algo <= 2 && n > 64 && n <= kLwmMaxN;
+}
+inline cudaError_t launch_lwm_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
+                                     unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    if (algo == 0) return launch_lwm_a0(n, batch, a, l, e, p, k, sms, st);
+    if (algo == 1) return launch_lwm_a1(n, batch, a, l, e, p, k, sms, st);
+    if (algo == 2) return launch_lwm_a2(n, batch, a, l, e, p, k, sms, st);
+    return cudaErrorNotSupported;
 }
 
 inline cudaError_t launch_warp_kernel(int algo, int mode, int n, long long batch, const double* a,

@@ -219,6 +219,33 @@ def test_fast_mode_within_north_star_tolerances(oracle, torch_cuda, algo, n):
         _assert_tolerance(f"{algo} n={n} {fam}", a, _gpu(torch_cuda, algo, a, "fast"), ref)
 
 
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("n", [129, 136, 200, 255, 256, 300, 384, 512, 1000])
+def test_fast_mode_large_blocked_kernels(oracle, torch_cuda, algo, n):
+    """The large size class (128 < n <= 1024, north star): blocked CTA-per-matrix kernels
+    (bsm_kernels.cuh) for all three algorithms, FAST bars against the oracle."""
+    assert m.kernel_class(algo, n, "fast") == "cta_blocked"
+    b = 6 if n <= 300 else 2
+    for fam in ("uniform", "wishart", "pd", "bench"):
+        a = matgen.make(fam, 4000 + n, b, n)
+        ref = oracle.factor_batched(algo, a)
+        _assert_tolerance(f"{algo} n={n} {fam}", a, _gpu(torch_cuda, algo, a, "fast"), ref,
+                          min_firm=0.4 if fam == "bench" else 0.9)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("n", [66, 97, 128, 130, 200, 250, 256])
+def test_fast_mode_warp_panel_kernels(oracle, torch_cuda, algo, n, monkeypatch):
+    """The opt-in warp-per-matrix panel kernels (lwm_kernels.cuh: trailing matrix streamed through
+    a cp.async.bulk / mbarrier ring): even n takes the bulk-copy path, odd n the ordinary one."""
+    monkeypatch.setenv("MODCHOL_LWM_MIN", "65")
+    assert m.kernel_class(algo, n, "fast") == "warp_panel"
+    for fam in ("uniform", "wishart", "pd"):
+        a = matgen.make(fam, 5000 + n, 6, n)
+        ref = oracle.factor_batched(algo, a)
+        _assert_tolerance(f"{algo} n={n} {fam} lwm", a, _gpu(torch_cuda, algo, a, "fast"), ref)
+
+
 @pytest.mark.parametrize("mode", ["strict", "fast"])
 def test_exact_ties_resolve_to_lowest_index(oracle, torch_cuda, mode):
     # equal diagonals -> lowest index wins (utils.rs:57-69); A6-like duplicated rows
