@@ -34,6 +34,11 @@ extern "C" {
         x: *mut f64, l: *mut f64, e: *mut f64, p: *mut u64, phase2_start: *mut i32,
         mem_kind: c_int, stream: *mut c_void,
     ) -> c_int;
+    pub fn modchol_assemble_qdqt_batched_f64(
+        batch: i64, n: i32, nrefl: i32, v: *const f64, d: *const f64, a: *mut f64, mem_kind: c_int,
+        stream: *mut c_void,
+    ) -> c_int;
+    pub fn modchol_fp64_peak_tflops(dfma_tflops: *mut f64, dmma_tflops: *mut f64) -> c_int;
     pub fn modchol_set_small_kernel_family(family: c_int) -> c_int;
     pub fn modchol_kernel_class(algo: c_int, mode: c_int, n: i32) -> *const c_char;
     pub fn modchol_launch_count() -> i64;

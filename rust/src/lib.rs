@@ -52,7 +52,7 @@ impl<L, E, P> Decomposition<L, E, P> {
     }
 }
 
-fn check(rc: c_int) {
+pub(crate) fn check(rc: c_int) {
     if rc != 0 {
         let msg = unsafe { CStr::from_ptr(ffi::modchol_last_error()) }.to_string_lossy().into_owned();
         // the reference's traits are infallible; it panics on misuse, and so do we

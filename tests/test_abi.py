@@ -47,6 +47,22 @@ def test_version_and_kernel_classes():
     assert m.kernel_class("se99", 4096) == "unsupported"
 
 
+def test_rust_facade_binds_every_entry_point():
+    """rust/src/ffi.rs cannot be compiled here (no rustc): at least every C-ABI function of the
+    header must be declared there with the same number of parameters."""
+    hdr = open(os.path.join(ROOT, "include", "modchol_b200.h")).read()
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    found = re.findall(r"\b(modchol_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert sorted(n for n, _ in found) == sorted(_lib.EXPORTS)
+    for name, cargs in found:
+        mm = re.search(r"pub fn %s\s*\(([^)]*)\)" % name, ffi, re.S)
+        assert mm, f"{name} is not declared in rust/src/ffi.rs"
+        nc = 0 if cargs.strip() in ("", "void") else cargs.count(",") + 1
+        rargs = mm.group(1).strip().rstrip(",")
+        nr = 0 if not rargs else rargs.count(",") + 1
+        assert nc == nr, f"{name}: {nc} parameters in the header, {nr} in ffi.rs"
+
+
 def test_bad_arguments_are_rejected_before_any_cuda_work():
     L = m.lib()
     a = np.zeros((1, 2, 2))
