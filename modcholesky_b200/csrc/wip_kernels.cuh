@@ -17,9 +17,10 @@
 //     per-step column write and the fragment load both conflict free.
 //   * L is written to TENSOR MEMORY: lane i stores L(i,t) at step t into its own TMEM lane,
 //     columns 2t..2t+1 (tcgen05.st, one instruction per step, off the shared-memory pipe), so
-//     finished entries never have to be protected from the dumps.  In the epilogue every lane
-//     reads its row back (tcgen05.ld), zeroes the entries beyond its final position and writes
-//     it to row pos of the output with 256-bit stores -- no un-permutation pass.
+//     finished entries never have to be protected from the dumps.  A finished row stores exact
+//     zeros, so its row of L ends at the diagonal (se99.rs:189-192) without a pass over it.  In
+//     the epilogue every lane reads its row back (tcgen05.ld) and writes it to row pos of the
+//     output with 256-bit stores -- no un-permutation pass.
 //   * pivot search: order-preserving integer keys + ONE REDUX when the high word of the
 //     maximum is unique (practically always); ties fall back to the full first-in-position
 //     search of utils.rs:52-91 on (hi, lo, pos).
@@ -29,6 +30,8 @@
 // with the oracle within the north-star tolerances, not bit for bit -- STRICT mode keeps the
 // position-ordered kernels of wsm_se.cuh / wsm_gmw.cuh.
 #pragma once
+#include <type_traits>
+
 #include "wsm_se.cuh"
 
 #ifndef MODCHOL_WIP_DMMA_SUM
@@ -43,7 +46,17 @@ constexpr int kWipPanelLd = 36;    // panel column stride: == 4 (mod 16) doubles
 #define MODCHOL_WIP_KB 8
 #endif
 constexpr int kWipKB = MODCHOL_WIP_KB;   // steps between two trailing updates (4 or 8)
-constexpr int kWipDoubles = kWipTri + kWipKB * kWipPanelLd;
+// Two layouts of the panel of pending columns, chosen per size class (measured, profiles/r02_notes.md):
+//   by columns (n > 24): column c at 8 c kWipPanelLd bytes, every lane keeps its own entries in
+//       registers, one LDS + FMA per pending column;
+//   by rows (n <= 24): row i at 8 i kWipRowLd bytes (80-byte rows: the 128-bit reads of a lane's own row
+//       are conflict free), no register copies, four pending columns per pair of 128-bit reads.
+#ifndef MODCHOL_WIP_ROWPANEL
+#define MODCHOL_WIP_ROWPANEL 2   /* 0 by columns, 1 by rows, 2 by rows for n <= 24 */
+#endif
+constexpr int kWipRowLd = kWipKB + 2;
+constexpr int kWipPanelDoubles = kWipKB * kWipPanelLd > 32 * kWipRowLd ? kWipKB * kWipPanelLd : 32 * kWipRowLd;
+constexpr int kWipDoubles = kWipTri + kWipPanelDoubles;
 constexpr int kWipWarps = 4;       // warp w of a block owns TMEM lanes [32 w, 32 w + 32)
 constexpr int kWipTmemCols = 64;   // 32 doubles of L per lane
 
@@ -175,6 +188,7 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
     extern __shared__ double sm[];
     __shared__ unsigned tmem_base;
     constexpr int kTiles = NB * (NB + 1) / 2;
+    constexpr bool kWipRowPanel = MODCHOL_WIP_ROWPANEL == 1 || (MODCHOL_WIP_ROWPANEL == 2 && NB <= 3);
     const int n = kN ? kN : n_rt;
     int lane = threadIdx.x & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(lane));   // pinned (see wsm_se.cuh)
@@ -200,7 +214,9 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
     asm volatile("mov.u32 %0, %0;" : "+r"(tib));
     const unsigned pcol = pnb + 8u * (unsigned)lane;         // this lane's entry of panel column 0
     const int r8 = lane >> 2, c4 = lane & 3;
-    const unsigned pf = pnb + 8u * (unsigned)(kWipPanelLd * c4 + r8);      // fragment source
+    const unsigned pf = kWipRowPanel ? pnb + 8u * (unsigned)(kWipRowLd * r8 + c4)
+                                     : pnb + 8u * (unsigned)(kWipPanelLd * c4 + r8);      // fragment source
+    const unsigned prow = pnb + 8u * (unsigned)(kWipRowLd * lane);         // row-major panel: this lane's row
     const unsigned fr0 = wb + 8u * (unsigned)(tri(r8) + 2 * c4);           // slot (r8, 2 c4)
     const bool pd0 = 2 * c4 <= r8, pd1 = 2 * c4 + 1 <= r8;                 // diagonal tiles: lower part
     const size_t nn = (size_t)n * n;
@@ -308,8 +324,12 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
             for (int h = 0; h < KC; ++h)
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
-                    const unsigned a = pf + 8u * (unsigned)(4 * kWipPanelLd * h) + 64u * q;
-                    frag[h][q] = cnt == kWipKB ? lds_f64(a) : lds_f64_or_zero(4 * h + c4 < cnt, a);
+                    if constexpr (kWipRowPanel) {   // columns not yet produced hold zeros
+                        frag[h][q] = lds_f64(pf + 8u * (unsigned)(8 * q * kWipRowLd + 4 * h));
+                    } else {
+                        const unsigned a = pf + 8u * (unsigned)(4 * kWipPanelLd * h) + 64u * q;
+                        frag[h][q] = cnt == kWipKB ? lds_f64(a) : lds_f64_or_zero(4 * h + c4 < cnt, a);
+                    }
                     nfrag[h][q] = wip_neg(frag[h][q]);
                 }
 #pragma unroll
@@ -345,11 +365,23 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                 dump();
             else
                 __syncwarp();
+            if constexpr (kWipRowPanel) {   // every lane clears its own panel row (read by no one else now)
+#pragma unroll
+                for (int c = 0; c < kWipKB; c += 2)
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %1};" :: "r"(prow + 8u * c), "d"(0.0) : "memory");
+                __syncwarp();
+            }
         };
         if constexpr (kRegC) {
             __syncwarp();   // the previous matrix's readers of the triangle are done
             dump();
         } else {
+            __syncwarp();
+        }
+        if constexpr (kWipRowPanel) {
+#pragma unroll
+            for (int c = 0; c < kWipKB; c += 2)
+                asm volatile("st.shared.v2.f64 [%0], {%1, %1};" :: "r"(prow + 8u * c), "d"(0.0) : "memory");
             __syncwarp();
         }
 
@@ -364,26 +396,69 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
             csr[c] = 0.0;
         bool win;
 
-        // current value of C(lane, r): stored slot minus the C pending panel columns
-        auto column = [&](auto ctag, int r) -> double {
-            constexpr int C = decltype(ctag)::value;
+        // current value of C(lane, r): stored slot minus the C pending panel columns.  C is a run-time
+        // count: one copy of every step in the instruction stream (eight unrolled copies, one per
+        // count, made the hot loop 50 KB of code and cost 2 stall cycles per issue in instruction
+        // fetch); the switch falls through the pending columns C-1 .. 0.
+        auto column = [&](auto C, int r) -> double {
             const unsigned tr = wb + 4u * (unsigned)(r * (r + 1));
             double col = lds_f64(lane > r ? tib + 8u * (unsigned)r : tr + 8u * (unsigned)lane);
+            if constexpr (kWipRowPanel) {
+                // row-major panel: this row's and the pivot row's entries of the pending columns as
+                // 128-bit reads (the pivot row's are broadcasts); columns not yet produced are zero,
+                // the upper half of the panel is skipped while it is empty
+                const unsigned pq = pnb + 8u * (unsigned)(kWipRowLd * r);
+                auto half = [&](unsigned off) {
+                    const double2 o0 = lds_v2f64(prow + off), o1 = lds_v2f64(prow + off + 16u);
+                    const double2 q0 = lds_v2f64(pq + off), q1 = lds_v2f64(pq + off + 16u);
+                    double s0 = dmul(o0.x, q0.x), s1 = dmul(o0.y, q0.y);
+                    s0 = __fma_rn(o1.x, q1.x, s0);
+                    s1 = __fma_rn(o1.y, q1.y, s1);
+                    col = dsub(col, dadd(s0, s1));
+                };
+                int cv;
+                if constexpr (std::is_integral_v<decltype(C)>) cv = C; else cv = decltype(C)::value;
+                if (cv > 0)
+                    half(0u);
+                if constexpr (kWipKB > 4)
+                    if (cv > 4)
+                        half(32u);
+                return col;
+            }
+            const unsigned pr = pnb + 8u * (unsigned)r;
+            if constexpr (!std::is_integral_v<decltype(C)>) {   // compile-time count (unrolled callers)
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-                col = __fma_rn(-csr[c], lds_f64(pnb + 8u * (unsigned)(kWipPanelLd * c + r)), col);
+                for (int c = 0; c < decltype(C)::value; ++c)
+                    col = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col);
+                return col;
+            } else {
+            auto corr = [&](auto ctag) {
+                constexpr int c = decltype(ctag)::value;
+                if constexpr (c < kWipKB - 1)
+                    col = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col);
+            };
+            // a tree of warp-uniform branches on the count (no jump table: its constant load and
+            // indirect branch sat on the step's critical path twice)
+            if (C >= 4) {
+                corr(IC<0>{}); corr(IC<1>{}); corr(IC<2>{}); corr(IC<3>{});
+                if (C >= 6) {
+                    corr(IC<4>{}); corr(IC<5>{});
+                    if (C >= 7)
+                        corr(IC<6>{});
+                } else if (C == 5) {
+                    corr(IC<4>{});
+                }
+            } else if (C >= 2) {
+                corr(IC<0>{}); corr(IC<1>{});
+                if (C == 3)
+                    corr(IC<2>{});
+            } else if (C == 1) {
+                corr(IC<0>{});
+            }
             return col;
+            }
         };
-        auto column_rt = [&](int c, int r) -> double {
-            double v = 0.0;
-            wip_steps<0, kWipKB>([&](auto ctag) {
-                if (c != decltype(ctag)::value)
-                    return false;
-                v = column(ctag, r);
-                return true;
-            });
-            return v;
-        };
+        auto column_rt = [&](int c, int r) -> double { return column(c, r); };
         // the pivot row r takes position j; the row that sat there takes r's old position
         auto take_position = [&](int r) {
             const int pr = __shfl_sync(kFull, pos, r);
@@ -392,12 +467,40 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
         };
         // column j of L: cs (sq for the pivot row) into tensor memory and panel column C;
         // row r is finished
-        auto retire = [&](auto ctag, int r, double cs, double sq) {
-            constexpr int C = decltype(ctag)::value;
+        auto retire = [&](auto C, int r, double cs, double sq) {
             wip_tmem_store(tw + 2u * (unsigned)j, lane == r ? sq : cs);
+            if constexpr (kWipRowPanel) {
+                int cv;
+                if constexpr (std::is_integral_v<decltype(C)>) cv = C; else cv = decltype(C)::value;
+                sts_f64(prow + 8u * (unsigned)cv, cs);
+            } else if constexpr (!std::is_integral_v<decltype(C)>) {
+                constexpr int kC = decltype(C)::value;
+                sts_f64(pcol + 8u * (unsigned)(kWipPanelLd * kC), cs);
+                if constexpr (kC < kWipKB - 1)
+                    csr[kC] = cs;
+            } else {
             sts_f64(pcol + 8u * (unsigned)(kWipPanelLd * C), cs);
-            if constexpr (C < kWipKB - 1)
-                csr[C] = cs;
+            auto keep = [&](auto ctag) {
+                constexpr int c = decltype(ctag)::value;
+                if constexpr (c < kWipKB - 1)
+                    csr[c] = cs;
+            };
+            if (C >= 4) {
+                if (C >= 6) {
+                    if (C == 6) keep(IC<6>{});
+                } else if (C == 5) {
+                    keep(IC<5>{});
+                } else {
+                    keep(IC<4>{});
+                }
+            } else if (C >= 2) {
+                if (C == 3) keep(IC<3>{}); else keep(IC<2>{});
+            } else if (C == 1) {
+                keep(IC<1>{});
+            } else {
+                keep(IC<0>{});
+            }
+            }
             fin = fin || lane == r;
             fmask |= 1u << r;
             __syncwarp();
@@ -447,11 +550,23 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                 double sq = dmul(dj, y);
                 if (!fast_range_ok(dj))
                     wip_slow_gmw(dj, sq, y);
-                const double cs = dmul(col, y);
-                dg = live ? __fma_rn(-cs, cs, dg) : dg;             // gmw81.rs:104-109
+                const double cs = fin ? 0.0 : dmul(col, y);         // finished rows receive exact zeros
+                dg = __fma_rn(-cs, cs, dg);                         // gmw81.rs:104-109 (no mask needed)
                 ev = lane == r ? dsub(dj, cjj) : ev;                // gmw81.rs:110
                 retire(ctag, r, cs, sq);
             };
+            // (one algorithm phase only: the eight unrolled copies of the step, one per count of
+            // pending columns, fit the instruction cache and save the dispatch on the count)
+            if constexpr (kWipRowPanel) {
+                while (j < n) {
+                    gmw_step(cnt);
+                    ++cnt;
+                    if (j < n && cnt == kWipKB) {
+                        rank_update(kWipKB);
+                        cnt = 0;
+                    }
+                }
+            } else {
             while (j < n) {
                 if (wip_steps<0, kWipKB>([&](auto ctag) {
                         gmw_step(ctag);
@@ -459,6 +574,7 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                     }))
                     break;
                 rank_update(kWipKB);
+            }
             }
         } else {
             double g = dsub(dg, asum);            // Gershgorin bound if phase 2 starts at column 0
@@ -507,19 +623,20 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                     kstart = j;
                     return 1;
                 }
-                dg = live ? dgn : dg;
+                cs = fin ? 0.0 : cs;
+                dg = dgn;   // (finished rows and the pivot row: never looked at again)
                 retire(ctag, r, cs, sq);
                 return j == n ? 2 : 0;
             };
             int st = 0;
             for (;;) {
-                if (wip_steps<0, kWipKB>([&](auto ctag) {
-                        cnt = decltype(ctag)::value;   // pending panel columns at this step
-                        st = p1_step(ctag);
-                        return st != 0;
-                    }))
+                st = p1_step(cnt);   // cnt: pending panel columns at this step
+                if (st != 0)
                     break;
-                rank_update(kWipKB);
+                if (++cnt == kWipKB) {
+                    rank_update(kWipKB);
+                    cnt = 0;
+                }
             }
 
             // ---- phase 2 -------------------------------------------------------------------
@@ -528,7 +645,7 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                 const double ljj = __shfl_sync(kFull, dg, u);
                 const double ej = tail1x1_e(ljj, gamma);
                 ev = lane == u ? ej : ev;
-                wip_tmem_store(tw + 2u * (unsigned)(n - 1), dsqrt(dadd(ljj, ej)));
+                wip_tmem_store(tw + 2u * (unsigned)(n - 1), lane == u ? dsqrt(dadd(ljj, ej)) : 0.0);
             } else if (st == 1) {
                 if (j > 0) {
                     // the Gershgorin bounds need the trailing block as the reference holds it: apply
@@ -572,20 +689,21 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                     double cs = dmul(col, y);
                     if (!fast_range_ok(piv))
                         wip_slow_p2(piv, normj, col, sq, t, cs);
-                    dg = live ? __fma_rn(-cs, cs, dg) : dg;
-                    g = (live && upd) ? __fma_rn(acol, t, g) : g;
+                    // finished rows receive exact zeros (their row of L in tensor memory ends at the
+                    // diagonal, se99.rs:189-192); their diagonal and bound are never looked at again,
+                    // so the updates below need no mask
+                    cs = fin ? 0.0 : cs;
+                    dg = __fma_rn(-cs, cs, dg);
+                    g = upd ? __fma_rn(acol, t, g) : g;
                     ev = lane == r ? ej : ev;
                     retire(ctag, r, cs, sq);
                 };
                 while (j + 2 < n) {
-                    if (wip_steps<0, kWipKB>([&](auto ctag) {
-                            p2_step(ctag);
-                            cnt = decltype(ctag)::value + 1;
-                            return cnt < kWipKB && j + 2 >= n;
-                        }))
-                        break;
-                    cnt = 0;
-                    rank_update(kWipKB);
+                    p2_step(cnt);
+                    if (++cnt == kWipKB) {
+                        rank_update(kWipKB);
+                        cnt = 0;
+                    }
                 }
                 // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186): the two rows
                 // alive sit at positions n-2 and n-1
@@ -606,8 +724,8 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                 a10 = ddiv(a10, a00);
                 a11 = dsqrt(dsub(a11, dmul(a10, a10)));
                 ev = (lane == u0 || lane == u1) ? en : ev;
-                wip_tmem_store(tw + 2u * (unsigned)(n - 2), lane == u0 ? a00 : a10);
-                wip_tmem_store(tw + 2u * (unsigned)(n - 1), a11);
+                wip_tmem_store(tw + 2u * (unsigned)(n - 2), lane == u0 ? a00 : (lane == u1 ? a10 : 0.0));
+                wip_tmem_store(tw + 2u * (unsigned)(n - 1), lane == u1 ? a11 : 0.0);
             }
         }
 
@@ -622,9 +740,7 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                     break;
                 double v[8];
                 wip_tmem_load8(tw + 16u * c, v);
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    v[u] = 8 * c + u <= pos ? v[u] : 0.0;
+                // (entries beyond the diagonal were stored as zeros: a finished row receives 0)
                 if (wide && has) {
                     stg_v4f64(dstp + 8 * c, v[0], v[1], v[2], v[3]);
                     stg_v4f64(dstp + 8 * c + 4, v[4], v[5], v[6], v[7]);
