@@ -343,20 +343,32 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                         for (int h = 0; h < KC; ++h)
                             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                                          : "+d"(cf[t][0]), "+d"(cf[t][1]) : "d"(nfrag[h][bi]), "d"(frag[h][bj]));
-                    } else {
-                        // (diagonal tiles: the entries above the diagonal are other rows' slots --
-                        // loaded, updated and not stored)
-                        double c0 = lds_f64(ra + 64u * bj), c1 = lds_f64(ra + 64u * bj + 8);
+                    }
+                }
+                if constexpr (!kRegC) {
+                    // (diagonal tiles: the entries above the diagonal are other rows' slots -- loaded,
+                    // updated and not stored.)  Per block row: every load first, then the tensor-pipe
+                    // operations, then the stores; the accessors are volatile asm, kept in program order
+                    double c0[NB], c1[NB];
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj) {
+                        c0[bj] = lds_f64(ra + 64u * bj);
+                        c1[bj] = lds_f64(ra + 64u * bj + 8);
+                    }
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj)
 #pragma unroll
                         for (int h = 0; h < KC; ++h)
                             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                                         : "+d"(c0), "+d"(c1) : "d"(nfrag[h][bi]), "d"(frag[h][bj]));
+                                         : "+d"(c0[bj]), "+d"(c1[bj]) : "d"(nfrag[h][bi]), "d"(frag[h][bj]));
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj) {
                         if (bi == bj) {
-                            sts_f64_if(pd0, ra + 64u * bj, c0);
-                            sts_f64_if(pd1, ra + 64u * bj + 8, c1);
+                            sts_f64_if(pd0, ra + 64u * bj, c0[bj]);
+                            sts_f64_if(pd1, ra + 64u * bj + 8, c1[bj]);
                         } else {
-                            sts_f64(ra + 64u * bj, c0);
-                            sts_f64(ra + 64u * bj + 8, c1);
+                            sts_f64(ra + 64u * bj, c0[bj]);
+                            sts_f64(ra + 64u * bj + 8, c1[bj]);
                         }
                     }
                 }

@@ -5,6 +5,7 @@
 
 #include "launch_cache.cuh"
 #include "warp_kernels.cuh"
+#include "wip2_kernels.cuh"
 #include "wip_kernels.cuh"
 #include "wsm_gmw.cuh"
 #include "wsm_se.cuh"
@@ -95,6 +96,46 @@ static cudaError_t launch_wip(int n, long long batch, const double* a, double* l
     return cudaGetLastError();
 }
 
+// FAST mode, 32 < n <= 64, no fused solve: the two-rows-per-lane implicit-pivoting kernels
+// (wip2_kernels.cuh); 256 tensor-memory columns and 84 KB of shared memory per block.
+template <int kAlgo, int NB, int kN>
+static cudaError_t launch_wip2(int n, long long batch, const double* a, double* l, double* e,
+                               unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    auto kern = wip2_kernel<kAlgo, NB, kN, 2>;
+    constexpr size_t smem = (size_t)kWipWarps * kWip2Doubles * sizeof(double);
+    static int occ_dev[64];
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    int occ = dev < 64 ? occ_dev[dev] : 0;
+    if (occ == 0) {
+        int ignored = 0;
+        ce = cached_occupancy(kern, kWipWarps * 32, smem, smem, &ignored);   // sets the attributes
+        if (ce != cudaSuccess) return ce;
+        cudaFuncAttributes fa;
+        ce = cudaFuncGetAttributes(&fa, kern);
+        if (ce != cudaSuccess) return ce;
+        const int by_regs = 65536 / (fa.numRegs * kWipWarps * 32);
+        const int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+        occ = by_regs < by_smem ? by_regs : by_smem;
+        if (occ < 1) occ = 1;
+        if (occ > 512 / kWip2TmemCols) occ = 512 / kWip2TmemCols;
+        if (dev < 64) occ_dev[dev] = occ;
+    }
+    long long blocks = (batch + kWipWarps - 1) / kWipWarps;
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
+    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    return cudaGetLastError();
+}
+
+static bool wip2_enabled()
+{
+    const char* v = getenv("MODCHOL_WIP2");
+    return !(v && v[0] == '0');
+}
+
 static bool wip_enabled()
 {
     const char* v = getenv("MODCHOL_WIP");
@@ -135,6 +176,10 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
     if (n <= 32)
         return wsm_pack_pref() ? launch_wsm<A, 16, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
                                : launch_wsm<A, 32, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
+    if (!S && x == nullptr && n > 32 && n <= 64 && wip2_enabled())
+        return n <= 48 ? launch_wip2<A, 6, 0>(n, batch, a, l, e, p, k, sms, st)
+               : n < 64 ? launch_wip2<A, 8, 0>(n, batch, a, l, e, p, k, sms, st)
+                        : launch_wip2<A, 8, 64>(n, batch, a, l, e, p, k, sms, st);
     return launch_wsm<A, 32, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
 }
 
