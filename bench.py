@@ -428,6 +428,18 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * eb * e2e_steps / float(dt.item())
+    # the trait path a reference user takes: pageable numpy input through Array3(...), outputs
+    # allocated by the call (the library bounces through cached pinned buffers); rank 0, N = 1
+    e2e_pageable = None
+    if rank == 0 and world == 1:
+        an = ah.numpy().copy()
+        arr = m.Array3(an, mode=args.mode)
+        arr.mod_cholesky_se99_batched()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            arr.mod_cholesky_se99_batched()
+        e2e_pageable = 2 * eb / (time.perf_counter() - t0)
+        del an, arr
     h2d = eb * N_MAT * N_MAT * 8
     d2h = eb * (N_MAT * N_MAT * 8 + N_MAT * 8 + N_MAT * 8)
 
@@ -455,6 +467,10 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "matrices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "batch_per_gpu": eb, "steps": e2e_steps,
+                "trait_path_pageable_numpy": e2e_pageable,
+                "host_ceiling": "profiles/r02_pcie_ceiling_{1,8}gpu.txt: pinned H2D+D2H at once tops out at 95.5 GB/s "
+                                "for one rank and 127.7 GB/s for eight (all GPUs behind NUMA node 0): 5.65 / 7.56 M "
+                                "matrices/s at 16 896 B per matrix",
                 "path": "modchol_factor_batched_f64(mem_kind=HOST): pinned host -> 3-slot overlapped "
                         "H2D / kernel / D2H pipeline -> pinned host"},
         "roofline": roofline,

@@ -64,14 +64,17 @@ def _env():
 def build_library(force: bool = False, verbose: bool = False, jobs: int | None = None,
                   variant: str | None = None, extra: list[str] | None = None) -> str:
     """variant: build into csrc/build_<variant>/ and libmodchol_b200.<variant>.so with the extra
-    nvcc flags (kernel-tuning experiments; selected at run time with MODCHOL_LIB)."""
-    global OBJ, LIB
+    nvcc flags (kernel-tuning experiments and the bounds-checked "dbg" build; selected at run
+    time with MODCHOL_LIB)."""
+    obj_dir, lib = OBJ, LIB
     if variant:
-        OBJ = os.path.join(CSRC, "build_" + variant)
-        LIB = os.path.join(CSRC, f"libmodchol_b200.{variant}.so")
+        obj_dir = os.path.join(CSRC, "build_" + variant)
+        lib = os.path.join(CSRC, f"libmodchol_b200.{variant}.so")
+        if not force and os.path.exists(lib) and all(os.path.getmtime(s) <= os.path.getmtime(lib) for s in sources()):
+            return lib
     elif not force and not is_stale():
-        return LIB
-    os.makedirs(OBJ, exist_ok=True)
+        return lib
+    os.makedirs(obj_dir, exist_ok=True)
     exe, env = nvcc(), _env()
 
     extra = (extra or []) + os.environ.get("MODCHOL_NVCC_EXTRA", "").split()   # e.g. -DMODCHOL_WIP_MINB=5
@@ -80,7 +83,7 @@ def build_library(force: bool = False, verbose: bool = False, jobs: int | None =
         src, obj, defs = unit
         defs = defs + extra
         cmd = [exe] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + [
-            "-c", "-o", os.path.join(OBJ, obj), os.path.join(CSRC, src)]
+            "-c", "-o", os.path.join(obj_dir, obj), os.path.join(CSRC, src)]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {obj}:\n{r.stdout}\n{r.stderr}")
@@ -91,8 +94,16 @@ def build_library(force: bool = False, verbose: bool = False, jobs: int | None =
     if verbose:
         for obj, log in logs:
             print(f"==== {obj}\n{log}")
-    subprocess.check_call([exe, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [os.path.join(OBJ, u[1]) for u in UNITS], env=env)
-    return LIB
+    subprocess.check_call([exe, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib]
+                          + [os.path.join(obj_dir, u[1]) for u in UNITS], env=env)
+    return lib
+
+
+DEBUG_VARIANT = ("dbg", ["-DMODCHOL_DEBUG_BOUNDS=1"])   # shared-memory accessors bounds-checked (wsm_se.cuh)
+
+
+def build_debug_library(force: bool = False) -> str:
+    return build_library(force=force, variant=DEBUG_VARIANT[0], extra=DEBUG_VARIANT[1])
 
 
 if __name__ == "__main__":

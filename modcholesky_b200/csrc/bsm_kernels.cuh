@@ -51,10 +51,12 @@ __host__ __device__ inline size_t bsm_smem_doubles(int n, int kb)
 
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v)
 {
+    smem_check(a, 4u);
     asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned lds_u32(unsigned a)
 {
+    smem_check(a, 4u);
     unsigned v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;

@@ -52,6 +52,7 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y)
 {
+    smem_check(a, 16u);
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(x), "d"(y) : "memory");
 }
 

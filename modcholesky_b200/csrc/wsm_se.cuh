@@ -19,6 +19,7 @@
 // Only the lower triangle of A is read (A symmetric), so DRAM reads drop below the
 // algorithmic 8 n^2 bytes.  Measurements and the optimisation log: profiles/r01_notes.md.
 #pragma once
+#include <cstdio>
 #include <type_traits>
 
 #include "warp_common.cuh"
@@ -116,24 +117,52 @@ __device__ __forceinline__ int wsm_argmax_first(unsigned mask, const double (&v)
 // Explicit 32-bit shared-window addressing.  With generic `double*` accesses the compiler keeps
 // re-deriving the shared window base (S2R / S2UR / ULEA) under register pressure; one `unsigned`
 // byte address per warp plus these accessors removes ~60 instructions per step.
-__device__ __forceinline__ double lds_f64(unsigned a)
+// -DMODCHOL_DEBUG_BOUNDS=1 (the "dbg" build of modcholesky_b200/build.py, run by
+// tests/test_parity_gpu.py::test_debug_bounds_build): every access through these accessors is
+// checked against the block's shared-memory window and its natural alignment and traps
+// otherwise -- the stand-in for compute-sanitizer, which is closed on the GPU pool.
+#ifndef MODCHOL_DEBUG_BOUNDS
+#define MODCHOL_DEBUG_BOUNDS 0
+#endif
+__device__ __forceinline__ void smem_check(unsigned a, unsigned bytes, int line = 0, const char* file = "")
 {
+#if MODCHOL_DEBUG_BOUNDS
+    // the accessors only ever address the block's DYNAMIC shared memory (it starts behind the
+    // system-reserved kilobyte and the kernel's static variables)
+    extern __shared__ double modchol_dyn_smem_base[];
+    const unsigned lo = (unsigned)__cvta_generic_to_shared(modchol_dyn_smem_base);
+    unsigned dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if ((a & (bytes - 1u)) != 0u || a < lo || a + bytes > lo + dyn) {
+        printf("modchol: shared-memory access out of bounds: address %u, %u bytes, window [%u, %u) (block %d thread %d, %s:%d)\n",
+               a, bytes, lo, lo + dyn, (int)blockIdx.x, (int)threadIdx.x, file, line);
+        asm volatile("trap;");
+    }
+#endif
+}
+__device__ __forceinline__ double lds_f64(unsigned a, int line = __builtin_LINE(), const char* file = __builtin_FILE())
+{
+    smem_check(a, 8u, line, file);
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ double2 lds_v2f64(unsigned a)
+__device__ __forceinline__ double2 lds_v2f64(unsigned a, int line = __builtin_LINE(), const char* file = __builtin_FILE())
 {
+    smem_check(a, 16u, line, file);
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ void sts_f64(unsigned a, double v)
+__device__ __forceinline__ void sts_f64(unsigned a, double v, int line = __builtin_LINE(), const char* file = __builtin_FILE())
 {
+    smem_check(a, 8u, line, file);
     asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory");
 }
-__device__ __forceinline__ void sts_f64_if(bool pred, unsigned a, double v)
+__device__ __forceinline__ void sts_f64_if(bool pred, unsigned a, double v, int line = __builtin_LINE(), const char* file = __builtin_FILE())
 {
+    if (pred)
+        smem_check(a, 8u, line, file);
     asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}"
                  :: "r"(a), "d"(v), "r"((int)pred) : "memory");
 }
@@ -163,8 +192,10 @@ __device__ __forceinline__ void sts_f64_if(bool pred, unsigned long long a, doub
 }
 
 // ld.shared.f64 where pred, else 0.0 -- one predicated load into a zeroed register
-__device__ __forceinline__ double lds_f64_or_zero(bool pred, unsigned a)
+__device__ __forceinline__ double lds_f64_or_zero(bool pred, unsigned a, int line = __builtin_LINE(), const char* file = __builtin_FILE())
 {
+    if (pred)
+        smem_check(a, 8u, line, file);
     double v;
     asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n mov.f64 %0, 0d0000000000000000;\n"
                  " @q ld.shared.f64 %0, [%1];\n}"

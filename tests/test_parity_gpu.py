@@ -642,6 +642,47 @@ def test_fp64_peak_probe(torch_cuda):
     assert 10.0 < dfma < 80.0 and 10.0 < dmma < 80.0, (dfma, dmma)
 
 
+def test_debug_bounds_build(torch_cuda):
+    """compute-sanitizer is closed on the GPU pool; its stand-in is the "dbg" build
+    (-DMODCHOL_DEBUG_BOUNDS=1): every shared-memory access of the kernels' accessors is checked
+    against the block's window and traps otherwise.  A parity subset over every kernel class runs
+    under it in a fresh process (MODCHOL_LIB selects the library at import time)."""
+    import os
+    import subprocess
+    import sys
+    from modcholesky_b200.build import CSRC, DEBUG_VARIANT
+    lib = os.path.join(CSRC, f"libmodchol_b200.{DEBUG_VARIANT[0]}.so")
+    if not os.path.exists(lib):
+        pytest.skip("debug build not present (python -c 'import __graft_entry__ as g; g.build()')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+import matgen, modcholesky_b200 as m, oracle
+oracle.build_oracle()
+assert 'dbg' in m._lib.LIB_PATH
+for n in (5, 16, 24, 32, 48, 64, 100, 160, 256, 300):
+    b = 8 if n <= 64 else 3
+    for algo in ('gmw81', 'se90', 'se99'):
+        for fam in ('uniform', 'wishart'):
+            a = matgen.make(fam, 7 + n, b, n)
+            ref = oracle.factor_batched(algo, a)
+            ad = torch.from_numpy(a).cuda()
+            print('case', algo, n, fam, flush=True)
+            d = m.factor_batched(algo, ad, mode='strict')
+            torch.cuda.synchronize()
+            assert np.array_equal(d.l.cpu().numpy(), ref.l, equal_nan=True), (algo, n, fam)
+            f = m.factor_batched(algo, ad, mode='fast')
+            r, fl = m.verify_batched(ad, f)
+            torch.cuda.synchronize()
+            assert int(fl.max()) == 0, (algo, n, fam)
+print('debug-bounds parity subset ok')
+""" % (root, root)
+    env = dict(os.environ, MODCHOL_LIB=lib)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "subset ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_zz_report_relaxed_bar_counts():
     """Not a check: prints how many FAST-mode comparisons of this session used one of the two
     GMW81-only relaxed bars of _assert_tolerance (run pytest with -s to see it)."""
