@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -384,19 +385,32 @@ int factor_host_on_device(int dev, int algo, int mode, long long batch, int n, c
     struct Pending { long long off = 0, cnt = 0; };
     Pending pend[kSlots];
     // results of the chunk a slot last worked on: wait for its stream, then (pageable caller) copy
-    // them out of the bounce buffers
+    // them out of the bounce buffers -- on a helper thread, so that the copy-out of chunk c runs
+    // beside the copy-in of chunk c + kSlots on the calling thread (the fresh output pages of a
+    // numpy / ndarray caller fault in on first touch, which makes the copy-out the slower half)
+    std::future<void> outcopy[kSlots];
+    auto wait_outcopy = [&](int si) {
+        if (outcopy[si].valid())
+            outcopy[si].get();
+    };
     auto retire = [&](int si) -> cudaError_t {
         Slot& s = c.slots[si];
+        wait_outcopy(si);
         const cudaError_t ce = cudaStreamSynchronize(s.stream);
         const Pending pd = pend[si];
         pend[si] = Pending();
         if (ce != cudaSuccess || pd.cnt == 0 || !bounce_out)
             return ce;
-        parallel_memcpy(l + (size_t)pd.off * nn, s.hl, (size_t)pd.cnt * nn * sizeof(double));
-        memcpy(e + (size_t)pd.off * n, s.he, (size_t)pd.cnt * n * sizeof(double));
-        memcpy(p + (size_t)pd.off * n, s.hp, (size_t)pd.cnt * n * sizeof(unsigned long long));
-        if (k)
-            memcpy(k + pd.off, s.hk, (size_t)pd.cnt * sizeof(int));
+        outcopy[si] = std::async(std::launch::async, [=, &s]() {
+            parallel_memcpy(l + (size_t)pd.off * nn, s.hl, (size_t)pd.cnt * nn * sizeof(double));
+            memcpy(e + (size_t)pd.off * n, s.he, (size_t)pd.cnt * n * sizeof(double));
+            memcpy(p + (size_t)pd.off * n, s.hp, (size_t)pd.cnt * n * sizeof(unsigned long long));
+            if (k)
+                memcpy(k + pd.off, s.hk, (size_t)pd.cnt * sizeof(int));
+        });
+        static const bool sync_out = getenv("MODCHOL_SYNC_OUTCOPY") != nullptr;   // A/B knob
+        if (sync_out)
+            wait_outcopy(si);
         return cudaSuccess;
     };
     cudaError_t ce = cudaSuccess;
@@ -421,6 +435,7 @@ int factor_host_on_device(int dev, int algo, int mode, long long batch, int n, c
         rc = factor_device(dev, algo, mode, cnt, n, s.a, s.l, s.e, s.p, k ? s.k : nullptr, s.stream);
         if (rc)
             break;
+        wait_outcopy(si);   // the slot's output bounce buffers are about to be overwritten
         double* dl = bounce_out ? s.hl : l + (size_t)off * nn;
         double* de = bounce_out ? s.he : e + (size_t)off * n;
         unsigned long long* dp = bounce_out ? s.hp : p + (size_t)off * n;
@@ -445,6 +460,8 @@ int factor_host_on_device(int dev, int algo, int mode, long long batch, int n, c
         else
             cudaStreamSynchronize(c.slots[si].stream);
     }
+    for (int si = 0; si < kSlots; ++si)
+        wait_outcopy(si);
     if (rc)
         return rc;
     if (ce != cudaSuccess)
