@@ -12,7 +12,8 @@ from .api import (  # noqa: F401
     Array2, Array3, Decomposition, assemble_qdqt_batched, fp64_peak_tflops, GershgorinCircles, ModCholeskyGMW81, ModCholeskySE90,
     ModCholeskySE99, NotSquareError, factor, factor_batched, factor_solve_batched,
     gershgorin_circles_batched,
-    mod_cholesky_gmw81, mod_cholesky_se90, mod_cholesky_se99, solve_batched, verify_batched)
+    mod_cholesky_gmw81, mod_cholesky_se90, mod_cholesky_se99, set_default_mode, solve_batched,
+    verify_batched)
 
 __version__ = "0.1.0"
 

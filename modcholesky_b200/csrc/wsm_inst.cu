@@ -7,6 +7,7 @@
 #include "warp_kernels.cuh"
 #include "wip2_kernels.cuh"
 #include "wip_kernels.cuh"
+#include "wipp_kernels.cuh"
 #include "wsm_gmw.cuh"
 #include "wsm_se.cuh"
 
@@ -130,6 +131,45 @@ static cudaError_t launch_wip2(int n, long long batch, const double* a, double* 
     return cudaGetLastError();
 }
 
+// FAST mode, 8 < n <= 16, no fused solve: two matrices per warp (wipp_kernels.cuh)
+template <int kAlgo, int kN>
+static cudaError_t launch_wipp(int n, long long batch, const double* a, double* l, double* e,
+                               unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    auto kern = wipp_kernel<kAlgo, kN, 8>;
+    constexpr size_t smem = (size_t)kWipWarps * 2 * kWppMat * sizeof(double);
+    static int occ_dev[64];
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    int occ = dev < 64 ? occ_dev[dev] : 0;
+    if (occ == 0) {
+        int ignored = 0;
+        ce = cached_occupancy(kern, kWipWarps * 32, smem, smem, &ignored);   // sets the attributes
+        if (ce != cudaSuccess) return ce;
+        cudaFuncAttributes fa;
+        ce = cudaFuncGetAttributes(&fa, kern);
+        if (ce != cudaSuccess) return ce;
+        const int by_regs = 65536 / (fa.numRegs * kWipWarps * 32);
+        const int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+        occ = by_regs < by_smem ? by_regs : by_smem;
+        if (occ < 1) occ = 1;
+        if (occ > 16) occ = 16;   // 64 warps per SM; 32 tensor-memory columns per block
+        if (dev < 64) occ_dev[dev] = occ;
+    }
+    long long blocks = (batch + kWipWarps * 2 - 1) / (kWipWarps * 2);
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
+    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    return cudaGetLastError();
+}
+
+static bool wipp_enabled()
+{
+    const char* v = getenv("MODCHOL_WIPP");
+    return !(v && v[0] == '0');
+}
+
 static bool wip2_enabled()
 {
     const char* v = getenv("MODCHOL_WIP2");
@@ -160,9 +200,9 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
 {
     constexpr int A = MODCHOL_INST_ALGO;
     constexpr bool S = MODCHOL_INST_STRICT != 0;
-    if (!S && x == nullptr && n > 12 && n <= 16 && wip_enabled())
-        return n < 16 ? launch_wip<A, 2, 0>(n, batch, a, l, e, p, k, sms, st)
-                      : launch_wip<A, 2, 16>(n, batch, a, l, e, p, k, sms, st);
+    if (!S && x == nullptr && n > 8 && n <= 16 && wipp_enabled())
+        return n < 16 ? launch_wipp<A, 0>(n, batch, a, l, e, p, k, sms, st)
+                      : launch_wipp<A, 16>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 4)
         return launch_wsm<A, 4, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 8)

@@ -210,9 +210,9 @@ def test_strict_bit_exact_large(oracle, torch_cuda, algo, n):
 
 
 @pytest.mark.parametrize("algo", ALGOS)
-@pytest.mark.parametrize("n", [2, 3, 6, 8, 13, 16, 24, 25, 32, 33, 40, 48, 49, 63, 64, 100, 150, 256])
+@pytest.mark.parametrize("n", [2, 3, 6, 8, 9, 10, 12, 13, 15, 16, 24, 25, 32, 33, 40, 48, 49, 63, 64, 100, 150, 256])
 def test_fast_mode_within_north_star_tolerances(oracle, torch_cuda, algo, n):
-    b = 512 if n <= 32 else (64 if n <= 64 else 16)
+    b = 511 if n <= 32 else (63 if n <= 64 else 16)   # odd: the last warp of a packed kernel is half empty
     for fam in ("uniform", "wishart", "pd", "bench"):
         a = matgen.make(fam, 3000 + n, b, n)
         ref = oracle.factor_batched(algo, a)
