@@ -8,7 +8,9 @@ sum r02_se99_n32_fast 131072 32
 python tools/ncu_hot.py $G/r02_se99_n32_fast.ncu-rep 131072 40 > $P/r02_se99_n32_fast_instmix.txt
 python tools/ncu_lines.py $G/r02_se99_n32_fast.ncu-rep 131072 80 > $P/r02_se99_n32_fast_lines.txt
 python tools/ncu_smem.py $G/r02_se99_n32_fast.ncu-rep 131072 20 > $P/r02_se99_n32_fast_smem.txt
+sum r02_se99_n32_fast_wishart 131072 32
 sum r02_se99_n32_strict 131072 32
+sum r02_verify_n32 131072 32
 sum r02_gmw81_n256_fast 1184 256
 BY_STALL=1 python tools/ncu_lines.py $G/r02_gmw81_n256_fast.ncu-rep 1184 30 > $P/r02_gmw81_n256_fast_lines.txt
 sum r02_se99_n256_fast 1184 256
@@ -50,4 +52,5 @@ json.dump({"source": "ncu --set full, profiles/r02_se99_n32_fast_summary.txt (wi
           open("profiles/r02_traffic.json", "w"), indent=1)
 PY
 cp $G/r02_sweep_a.txt $P/r02_size_sweep.txt
+[ -f $G/r02_sweep_warp_panel.txt ] && cp $G/r02_sweep_warp_panel.txt $P/r02_size_sweep_warp_panel.txt
 ls $P | grep r02

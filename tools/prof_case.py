@@ -13,5 +13,6 @@ reps = int(sys.argv[6]) if len(sys.argv) > 6 else 3
 a = gen(fam, batch, n)
 for _ in range(reps):
     d = m.factor_batched(algo, a, mode=mode)
+    r = m.verify_batched(a, d)   # the on-device acceptance check is part of the profiled command
 torch.cuda.synchronize()
 print("ok", algo, n, batch, fam, mode, m.kernel_class(algo, n, mode))
