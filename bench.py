@@ -287,9 +287,20 @@ def run_reference(args):
     if rank != 0:
         return 0
     import numpy as np
-    rng = np.random.default_rng(SEED)
-    a = rng.uniform(-1, 1, size=(CPU_SAMPLE, N_MAT, N_MAT))
-    a = np.tril(a) + np.transpose(np.tril(a, -1), (0, 2, 1))
+    sample_src = "numpy default_rng"
+    a = None
+    try:   # the same bytes as the first CPU_SAMPLE matrices of the CUDA arm's batch on rank 0
+        import torch
+        if torch.cuda.is_available():
+            a = gen_batch(torch, CPU_SAMPLE, N_MAT, SEED, torch.device("cuda", 0)).cpu().numpy()
+            sample_src = "the first matrices of the CUDA arm's rank-0 batch (same generator, same seed)"
+            torch.cuda.empty_cache()
+    except Exception:
+        a = None
+    if a is None:
+        rng = np.random.default_rng(SEED)
+        a = rng.uniform(-1, 1, size=(CPU_SAMPLE, N_MAT, N_MAT))
+        a = np.tril(a) + np.transpose(np.tril(a, -1), (0, 2, 1))
     for _ in range(max(args.warmup, 1)):
         cpu_baseline(a[: CPU_SAMPLE // 8])
     t0 = time.perf_counter()
@@ -306,8 +317,8 @@ def run_reference(args):
         "config": {"workload": f"se99 n={N_MAT} symmetric-uniform, {CPU_SAMPLE} matrices per step "
                                f"(bounded sample of the 2^20-per-GPU workload)", "algo": ALGO, "n": N_MAT},
         "cpu_baseline": {"value": value, "unit": "matrices/s", "cores": threads, "kind": "port",
-                         "sample": f"{CPU_SAMPLE} matrices x {args.steps} steps, C restatement of the "
-                                   f"reference (Rust toolchain absent), pthreads over the batch"},
+                         "sample": f"{CPU_SAMPLE} matrices x {args.steps} steps ({sample_src}), C restatement of "
+                                   f"the reference (Rust toolchain absent), pthreads over the batch"},
         "e2e": {"value": value, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
