@@ -8,9 +8,9 @@
 //     retire column j in the same iteration, whatever phase each is in, so the trailing update
 //     (mma.sync.m8n8k4.f64 needs the whole warp) and the tensor-memory store of column j of L
 //     (tcgen05.st is warp-wide) sit at convergence points of the loop;
-//   * every collective is issued with the FULL member mask and is segmented by hand (a .sync
-//     intrinsic whose mask differs between the halves of a warp is executed once per distinct
-//     mask: the first version ran every step twice): two REDUX (one per group) instead of one,
+//   * every collective is issued with the FULL member mask and is segmented by hand (the first
+//     version, on 16-lane member masks with per-group branches, ran every step once per group:
+//     1 950 warp-instructions per matrix against 1 899 unpacked): two REDUX (one per group),
 //     ballots split in halves, shuffles with a per-lane source.  All control flow is warp-uniform:
 //     the code of a phase runs when ANY group is in that phase, with the other group's updates
 //     predicated off;

@@ -17,7 +17,7 @@ import test_parity_gpu as T
 
 nmax = int(sys.argv[1]) if len(sys.argv) > 1 else 72
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 7
-sizes = list(range(1, nmax + 1)) + [80, 96, 113, 128, 130, 177, 233, 240, 256]
+sizes = list(range(1, nmax + 1)) + [80, 96, 113, 128, 130, 177, 233, 240, 256, 290, 384, 513]
 bad = 0
 cases = 0
 for n in sizes:
