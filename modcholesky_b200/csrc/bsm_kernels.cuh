@@ -33,6 +33,8 @@
 namespace modchol {
 
 constexpr int kBsmMaxWarps = 32;
+// doubles of dynamic shared memory: scratch + diagonal + column line + panel
+constexpr unsigned kBsmScratchBytes = 4u * 192u + 8u * 64u + 8u * 8u + 16u + 48u;   // reductions, scalars, mbarrier; 1 408
 
 // panel column stride (doubles): >= n rounded up to 8, == 4 (mod 16): the per-step column
 // write (thread = row) and the DMMA fragment loads are both conflict free
@@ -46,7 +48,7 @@ __host__ __device__ inline int bsm_ldp(int n)
 // doubles of dynamic shared memory: panel + diagonal + column line + exchange scratch + mbarrier
 __host__ __device__ inline size_t bsm_smem_doubles(int n, int kb)
 {
-    return (size_t)kb * bsm_ldp(n) + 2 * (size_t)((n + 7) & ~7) + 3 * 2 * kBsmMaxWarps + 16 + 2;
+    return (size_t)kb * bsm_ldp(n) + 2 * (size_t)((n + 7) & ~7) + kBsmScratchBytes / 8;
 }
 
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v)
@@ -278,14 +280,16 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
     const int ldp = bsm_ldp(n);
     const int npad = (n + 7) & ~7;
     const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
-    const unsigned pb = smb;                                        // panel: column c at pb + 8 c ldp
-    const unsigned tdb = pb + 8u * (unsigned)(KB * ldp);            // diagonal of T, by position
-    const unsigned lineb = tdb + 8u * (unsigned)npad;               // pivot column, staged by bulk copy
+    // fixed-size scratch first (its addresses are the block's base plus constants: nothing to
+    // recompute inside the loops), then the diagonal, the column line and the panel
     BsmScratch sc;
-    sc.base = lineb + 8u * (unsigned)npad;
+    sc.base = smb;
     sc.buf = 0;
-    const unsigned scalb = sc.base + 4u * 192u + 8u * 64u;          // 8 doubles of scalars
+    const unsigned scalb = smb + 4u * 192u + 8u * 64u;              // 8 doubles of scalars
     const unsigned mbar = scalb + 8u * 8u;                          // one mbarrier
+    const unsigned tdb = smb + kBsmScratchBytes;                    // diagonal of T, by position
+    const unsigned lineb = tdb + 8u * (unsigned)npad;               // pivot column line
+    const unsigned pb = lineb + 8u * (unsigned)npad;                // panel: column c at pb + 8 c ldp
     const size_t nn = (size_t)n * n;
     const int row = tid;
     const bool rv = row < n;
@@ -372,22 +376,23 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
                 // left-looking inside the panel: minus P(i, 0..c) . P(j, 0..c), accumulated apart
                 // from the loaded element so that the products overlap the round trip to L2
                 if (rv && row >= j) {
-                    const double* pr = sm + prow;                   // panel column t at sm + t ldp
-                    const double* pq = sm + pj;
+                    unsigned pr = pb + 8u * (unsigned)prow;         // panel column t at pb + 8 t ldp
+                    unsigned pq = pb + 8u * (unsigned)pj;
+                    const unsigned st8 = 8u * (unsigned)ldp;
                     double s0 = 0.0, s1 = 0.0;
                     int t = 0;
-                    for (; t + 4 <= c; t += 4) {
-                        const double r0 = pr[(t + 0) * ldp], r1 = pr[(t + 1) * ldp];
-                        const double r2 = pr[(t + 2) * ldp], r3 = pr[(t + 3) * ldp];
-                        const double q0 = pq[(t + 0) * ldp], q1 = pq[(t + 1) * ldp];
-                        const double q2 = pq[(t + 2) * ldp], q3 = pq[(t + 3) * ldp];
+                    for (; t + 4 <= c; t += 4, pr += 4u * st8, pq += 4u * st8) {
+                        const double r0 = lds_f64(pr), r1 = lds_f64(pr + st8);
+                        const double r2 = lds_f64(pr + 2u * st8), r3 = lds_f64(pr + 3u * st8);
+                        const double q0 = lds_f64(pq), q1 = lds_f64(pq + st8);
+                        const double q2 = lds_f64(pq + 2u * st8), q3 = lds_f64(pq + 3u * st8);
                         s0 = __fma_rn(r0, q0, s0);
                         s1 = __fma_rn(r1, q1, s1);
                         s0 = __fma_rn(r2, q2, s0);
                         s1 = __fma_rn(r3, q3, s1);
                     }
-                    for (; t < c; ++t)
-                        s0 = __fma_rn(pr[t * ldp], pq[t * ldp], s0);
+                    for (; t < c; ++t, pr += st8, pq += st8)
+                        s0 = __fma_rn(lds_f64(pr), lds_f64(pq), s0);
                     col = dsub(col, dadd(s0, s1));
                 }
                 if (row == j)
@@ -424,7 +429,9 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
                     }
                 }
                 const double tb = dmul(theta, rbeta);
-                const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
+                // gmw81.rs:102; delta and (theta/beta)^2 are never NaN here, so `a > b ? a : b` with the
+                // possibly-NaN value on the left is f64::max at a third of the instructions
+                const double dj = max_b_not_nan(max_b_not_nan(fabs(cjj), dmul(tb, tb)), delta);
                 double yy = rsqrt_normal(dj);
                 double sq = dmul(dj, yy);
                 if (!fast_range_ok(dj))
@@ -486,13 +493,13 @@ bsm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
     const int ldp = bsm_ldp(n);
     const int npad = (n + 7) & ~7;
     const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
-    const unsigned pb = smb;                                        // panel: column c at pb + 8 c ldp
-    const unsigned tdb = pb + 8u * (unsigned)(KB * ldp);            // diagonal of T (trailing-update bookkeeping)
-    const unsigned lineb = tdb + 8u * (unsigned)npad;
-    BsmScratch sc;
-    sc.base = lineb + 8u * (unsigned)npad;
+    BsmScratch sc;                                                  // layout: see bsm_gmw_kernel
+    sc.base = smb;
     sc.buf = 0;
-    const unsigned scalb = sc.base + 4u * 192u + 8u * 64u;          // 8 doubles of scalars
+    const unsigned scalb = smb + 4u * 192u + 8u * 64u;              // 8 doubles of scalars
+    const unsigned tdb = smb + kBsmScratchBytes;                    // diagonal of T (trailing-update bookkeeping)
+    const unsigned lineb = tdb + 8u * (unsigned)npad;
+    const unsigned pb = lineb + 8u * (unsigned)npad;                // panel: column c at pb + 8 c ldp
     const size_t nn = (size_t)n * n;
     const int row = tid;
     const bool rv = row < n;
@@ -550,22 +557,23 @@ bsm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
                 sts_f64(q + 16, g);
             }
             if (rv && row > j) {
-                const double* pr = sm + prow;
-                const double* pq = sm + pj;
+                unsigned pr = pb + 8u * (unsigned)prow;
+                unsigned pq = pb + 8u * (unsigned)pj;
+                const unsigned st8 = 8u * (unsigned)ldp;
                 double s0 = 0.0, s1 = 0.0;
                 int t = 0;
-                for (; t + 4 <= c; t += 4) {
-                    const double r0 = pr[(t + 0) * ldp], r1 = pr[(t + 1) * ldp];
-                    const double r2 = pr[(t + 2) * ldp], r3 = pr[(t + 3) * ldp];
-                    const double q0 = pq[(t + 0) * ldp], q1 = pq[(t + 1) * ldp];
-                    const double q2 = pq[(t + 2) * ldp], q3 = pq[(t + 3) * ldp];
+                for (; t + 4 <= c; t += 4, pr += 4u * st8, pq += 4u * st8) {
+                    const double r0 = lds_f64(pr), r1 = lds_f64(pr + st8);
+                    const double r2 = lds_f64(pr + 2u * st8), r3 = lds_f64(pr + 3u * st8);
+                    const double q0 = lds_f64(pq), q1 = lds_f64(pq + st8);
+                    const double q2 = lds_f64(pq + 2u * st8), q3 = lds_f64(pq + 3u * st8);
                     s0 = __fma_rn(r0, q0, s0);
                     s1 = __fma_rn(r1, q1, s1);
                     s0 = __fma_rn(r2, q2, s0);
                     s1 = __fma_rn(r3, q3, s1);
                 }
-                for (; t < c; ++t)
-                    s0 = __fma_rn(pr[t * ldp], pq[t * ldp], s0);
+                for (; t < c; ++t, pr += st8, pq += st8)
+                    s0 = __fma_rn(lds_f64(pr), lds_f64(pq), s0);
                 col = dsub(col, dadd(s0, s1));
             }
             if (tsw) {
