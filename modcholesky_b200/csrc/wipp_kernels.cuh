@@ -1,7 +1,8 @@
-// wipp_kernels.cuh -- the implicit-pivoting FAST kernels of wip_kernels.cuh for 8 < n <= 16 with
-// TWO matrices per warp: lanes 0-15 own the rows of one matrix, lanes 16-31 those of another
-// (gmw81.rs:39-134, se90.rs:38-181, se99.rs:35-201).  With one matrix per warp half the lanes idle
-// through every step of an n = 16 factorisation; here every lane works.
+// wipp_kernels.cuh -- the implicit-pivoting FAST kernels of wip_kernels.cuh for 4 < n <= 16 with
+// SEVERAL matrices per warp: G = 16 lanes per matrix (two matrices, 8 < n <= 16) or G = 8 (four
+// matrices, 4 < n <= 8); lane g G + i owns row i of the warp's g-th matrix (gmw81.rs:39-134,
+// se90.rs:38-181, se99.rs:35-201).  With one matrix per warp half (or three quarters) of the
+// lanes idle through every step; here every lane works.
 //
 // What is warp-wide and what is per group of 16 lanes:
 //   * the step counter j and the count of pending panel columns are warp-uniform: both matrices
@@ -18,9 +19,9 @@
 //     divergent code): the Gershgorin bounds (se90.rs:105-110, se99.rs:125-130) are formed from
 //     the stored slots minus the pending columns, element by element -- a cold path;
 //   * norms use a shuffle tree over the 16 lanes (the DMMA sum of wip_kernels.cuh is warp-wide).
-// Storage per matrix: packed lower triangle T(16) = 136 doubles, a row-major panel of the
-// pending columns (16 rows of kWppRowLd doubles, 128-bit reads conflict free), L in tensor
-// memory (32 columns per lane).
+// Storage per matrix: packed lower triangle T(G) doubles, a row-major panel of the pending
+// columns (G rows of kWppRowLd doubles, 128-bit reads conflict free), L in tensor memory (2 G
+// columns per lane).
 #pragma once
 #include "wip_kernels.cuh"
 
@@ -28,55 +29,88 @@ namespace modchol {
 
 constexpr int kWppKB = 4;                 // steps between two trailing updates
 constexpr int kWppRowLd = kWppKB + 2;     // 48-byte panel rows
-constexpr int kWppTri = 136;              // T(16)
-constexpr int kWppMat = kWppTri + 16 * kWppRowLd;   // doubles per matrix
 constexpr int kWppTmemCols = 32;
+// doubles per matrix: triangle + panel, padded so that consecutive matrices start 64 bytes apart
+// modulo 128 (two groups share a shared-memory wavefront of 8-byte accesses)
+__host__ __device__ constexpr int wpp_mat_doubles(int G) { return G == 16 ? 232 : ((G * (G + 1) / 2 + G * kWppRowLd + 15) & ~15) + 8; }
 
-// ---- collectives over the two 16-lane groups of a warp, both at once, full member mask --------
+// ---- collectives over the 32/G groups of a warp, all at once, full member mask ----------------
+template <int G>
 __device__ __forceinline__ int seg_max_s32(int grp, int v)
 {
-    const int r0 = __reduce_max_sync(kFull, grp == 0 ? v : (int)0x80000000);
-    const int r1 = __reduce_max_sync(kFull, grp == 1 ? v : (int)0x80000000);
-    return grp ? r1 : r0;
+    if constexpr (G == 16) {
+        const int r0 = __reduce_max_sync(kFull, grp == 0 ? v : (int)0x80000000);
+        const int r1 = __reduce_max_sync(kFull, grp == 1 ? v : (int)0x80000000);
+        return grp ? r1 : r0;
+    }
+    int mine = __reduce_max_sync(kFull, grp == 0 ? v : (int)0x80000000);
+#pragma unroll
+    for (int q = 1; q < 32 / G; ++q) {
+        const int r = __reduce_max_sync(kFull, grp == q ? v : (int)0x80000000);
+        mine = grp == q ? r : mine;
+    }
+    return mine;
 }
+template <int G>
 __device__ __forceinline__ unsigned seg_max_u32(int grp, unsigned v)
 {
-    const unsigned r0 = __reduce_max_sync(kFull, grp == 0 ? v : 0u);
-    const unsigned r1 = __reduce_max_sync(kFull, grp == 1 ? v : 0u);
-    return grp ? r1 : r0;
+    if constexpr (G == 16) {
+        const unsigned r0 = __reduce_max_sync(kFull, grp == 0 ? v : 0u);
+        const unsigned r1 = __reduce_max_sync(kFull, grp == 1 ? v : 0u);
+        return grp ? r1 : r0;
+    }
+    unsigned mine = __reduce_max_sync(kFull, grp == 0 ? v : 0u);
+#pragma unroll
+    for (int q = 1; q < 32 / G; ++q) {
+        const unsigned r = __reduce_max_sync(kFull, grp == q ? v : 0u);
+        mine = grp == q ? r : mine;
+    }
+    return mine;
 }
+template <int G>
 __device__ __forceinline__ unsigned seg_min_u32(int grp, unsigned v)
 {
-    const unsigned r0 = __reduce_min_sync(kFull, grp == 0 ? v : 0xffffffffu);
-    const unsigned r1 = __reduce_min_sync(kFull, grp == 1 ? v : 0xffffffffu);
-    return grp ? r1 : r0;
+    if constexpr (G == 16) {
+        const unsigned r0 = __reduce_min_sync(kFull, grp == 0 ? v : 0xffffffffu);
+        const unsigned r1 = __reduce_min_sync(kFull, grp == 1 ? v : 0xffffffffu);
+        return grp ? r1 : r0;
+    }
+    unsigned mine = __reduce_min_sync(kFull, grp == 0 ? v : 0xffffffffu);
+#pragma unroll
+    for (int q = 1; q < 32 / G; ++q) {
+        const unsigned r = __reduce_min_sync(kFull, grp == q ? v : 0xffffffffu);
+        mine = grp == q ? r : mine;
+    }
+    return mine;
 }
-// this group's half of a ballot, as bits of ABSOLUTE lane numbers
-__device__ __forceinline__ unsigned seg_ballot(int grp, bool pred)
+// this group's part of a ballot, as bits of ABSOLUTE lane numbers
+// (gbits: the lanes of this group, computed once per kernel)
+__device__ __forceinline__ unsigned seg_ballot(unsigned gbits, bool pred)
 {
-    return __ballot_sync(kFull, pred) & (0xffffu << (16 * grp));
+    return __ballot_sync(kFull, pred) & gbits;
 }
 
 // lane (absolute) of the first maximum in permuted-position order (utils.rs:52-91) over the
 // candidate lanes of each group; no candidate: the row at position j stays
-__device__ __forceinline__ int wipp_pivot_lane(int grp, int khi, unsigned klo, bool cand, bool fin, int pos, int j)
+template <int G>
+__device__ __forceinline__ int wipp_pivot_lane(int grp, unsigned gbits, int khi, unsigned klo, bool cand, bool fin, int pos, int j)
 {
-    const int mh = seg_max_s32(grp, cand ? khi : (int)0x80000000);
+    const int mh = seg_max_s32<G>(grp, cand ? khi : (int)0x80000000);
     const bool c1 = cand && khi == mh;
-    unsigned b1 = seg_ballot(grp, c1);
+    unsigned b1 = seg_ballot(gbits, c1);
     if (__any_sync(kFull, __popc(b1) != 1)) {
-        const unsigned ml = seg_max_u32(grp, c1 ? klo : 0u);
+        const unsigned ml = seg_max_u32<G>(grp, c1 ? klo : 0u);
         const bool win = c1 && klo == ml;
-        unsigned mpos = seg_min_u32(grp, win ? (unsigned)pos : 1024u);
+        unsigned mpos = seg_min_u32<G>(grp, win ? (unsigned)pos : 1024u);
         if (mpos > 255u)
             mpos = (unsigned)j;
-        b1 = seg_ballot(grp, !fin && pos == (int)mpos);
+        b1 = seg_ballot(gbits, !fin && pos == (int)mpos);
     }
-    return b1 ? 31 - __clz(b1) : 16 * grp;   // (a group without any row alive: any of its lanes)
+    return b1 ? 31 - __clz(b1) : G * grp;   // (a group without any row alive: any of its lanes)
 }
 
 // max (kMax) / min over the candidate lanes of each group, NaN never taken, `none` without candidates
-template <bool kMax>
+template <bool kMax, int G>
 __device__ __forceinline__ double seg_extreme(int grp, double v, bool cand, double none)
 {
     int khi;
@@ -87,22 +121,23 @@ __device__ __forceinline__ double seg_extreme(int grp, double v, bool cand, doub
         khi = ~khi;
         klo = ~klo;
     }
-    const int mh = seg_max_s32(grp, cand ? khi : (int)0x80000000);
-    const unsigned ml = seg_max_u32(grp, (cand && khi == mh) ? klo : 0u);
+    const int mh = seg_max_s32<G>(grp, cand ? khi : (int)0x80000000);
+    const unsigned ml = seg_max_u32<G>(grp, (cand && khi == mh) ? klo : 0u);
     if (mh == (int)0x80000000)
         return none;
     return kMax ? key_value(mh, ml) : key_value(~mh, ~ml);
 }
 
-__device__ __forceinline__ double wipp_sum16(double x)
+template <int G>
+__device__ __forceinline__ double wipp_sum(double x)
 {
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1)
+    for (int o = G / 2; o > 0; o >>= 1)
         x = dadd(x, __shfl_xor_sync(kFull, x, o));
     return x;
 }
 
-template <int kAlgo, int kN, int kMinBlocks>
+template <int kAlgo, int G, int kN, int kMinBlocks>
 __global__ void __launch_bounds__(kWipWarps * 32, kMinBlocks)
 wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __restrict__ L,
             double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
@@ -111,9 +146,16 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
     __shared__ unsigned tmem_base;
     const int n = kN ? kN : n_rt;
     int lane = threadIdx.x & 31;
-    asm volatile("mov.u32 %0, %0;" : "+r"(lane));
+    // through a shuffle: ptxas cannot re-derive the lane number (and the group index and masks that
+    // follow from it) from S2R inside the step loop, as it does under register pressure otherwise
+    lane = __shfl_sync(kFull, lane, lane);
     const int wib = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
-    const int sub = lane & 15, grp = lane >> 4;
+    constexpr int kGroups = 32 / G;           // matrices per warp
+    constexpr int NB = G / 8;                 // 8x8 block rows per matrix
+    constexpr int kWppTri = G * (G + 1) / 2;
+    constexpr int kWppMat = wpp_mat_doubles(G);
+    const int sub = lane & (G - 1), grp = lane / G;
+    const unsigned gbits = ((1u << G) - 1u) << (G * grp);   // the lanes of this group
 
     if (wib == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -125,7 +167,7 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tw = tmem_base + ((unsigned)(wib * 32) << 16);
 
-    unsigned wbw = (unsigned)__cvta_generic_to_shared(sm + (size_t)wib * 2 * kWppMat);   // this warp's two matrices
+    unsigned wbw = (unsigned)__cvta_generic_to_shared(sm + (size_t)wib * kGroups * kWppMat);   // this warp's matrices
     asm volatile("mov.u32 %0, %0;" : "+r"(wbw));
     const unsigned wb = wbw + 8u * (unsigned)(grp * kWppMat);     // this group's matrix
     const unsigned pnb = wb + 8u * kWppTri;                       // its panel
@@ -134,10 +176,10 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
     const int r8 = lane >> 2, c4 = lane & 3;
     const bool pd0 = 2 * c4 <= r8, pd1 = 2 * c4 + 1 <= r8;
     const size_t nn = (size_t)n * n;
-    const long long nslots = (long long)gridDim.x * kWipWarps * 2;
+    const long long nslots = (long long)gridDim.x * kWipWarps * kGroups;
     const bool wide = kN != 0 && kN % 8 == 0 && (((size_t)A | (size_t)L) & 31) == 0;
 
-    for (long long b0 = ((long long)blockIdx.x * kWipWarps + wib) * 2; b0 < batch; b0 += nslots) {
+    for (long long b0 = ((long long)blockIdx.x * kWipWarps + wib) * kGroups; b0 < batch; b0 += nslots) {
         const long long b = b0 + grp;
         const bool gact = b < batch;              // this group has a matrix
         const bool has = gact && sub < n;
@@ -186,31 +228,68 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         // lane clears its own panel row
         auto rank_update = [&]() {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < kGroups; ++m) {
                 const unsigned mb = wbw + 8u * (unsigned)(m * kWppMat);
                 const unsigned pf = mb + 8u * (unsigned)(kWppTri + kWppRowLd * r8 + c4);
                 const unsigned fr0 = mb + 8u * (unsigned)(tri(r8) + 2 * c4);
-                double f[2], c0[3], c1[3];
+                if constexpr (NB == 2) {
+                    double f[2], c0[3], c1[3];
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+                    for (int q = 0; q < 2; ++q)
+                        f[q] = lds_f64(pf + 8u * (unsigned)(8 * q * kWppRowLd));
+                    const unsigned ra1 = fr0 + 8u * (unsigned)(tri(8) + 8 * r8);
+                    c0[0] = lds_f64(fr0);        c1[0] = lds_f64(fr0 + 8);         // tile (0,0)
+                    c0[1] = lds_f64(ra1);        c1[1] = lds_f64(ra1 + 8);         // tile (1,0)
+                    c0[2] = lds_f64(ra1 + 64u);  c1[2] = lds_f64(ra1 + 72u);       // tile (1,1)
+                    const double nf0 = wip_neg(f[0]), nf1 = wip_neg(f[1]);
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c0[0]), "+d"(c1[0]) : "d"(nf0), "d"(f[0]));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c0[1]), "+d"(c1[1]) : "d"(nf1), "d"(f[0]));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c0[2]), "+d"(c1[2]) : "d"(nf1), "d"(f[1]));
+                    sts_f64_if(pd0, fr0, c0[0]);
+                    sts_f64_if(pd1, fr0 + 8, c1[0]);
+                    sts_f64(ra1, c0[1]);
+                    sts_f64(ra1 + 8, c1[1]);
+                    sts_f64_if(pd0, ra1 + 64u, c0[2]);
+                    sts_f64_if(pd1, ra1 + 72u, c1[2]);
+                    continue;
+                }
+                double f[NB], c0[NB * (NB + 1) / 2], c1[NB * (NB + 1) / 2];
+#pragma unroll
+                for (int q = 0; q < NB; ++q)
                     f[q] = lds_f64(pf + 8u * (unsigned)(8 * q * kWppRowLd));
-                const unsigned ra1 = fr0 + 8u * (unsigned)(tri(8) + 8 * r8);
-                c0[0] = lds_f64(fr0);        c1[0] = lds_f64(fr0 + 8);         // tile (0,0)
-                c0[1] = lds_f64(ra1);        c1[1] = lds_f64(ra1 + 8);         // tile (1,0)
-                c0[2] = lds_f64(ra1 + 64u);  c1[2] = lds_f64(ra1 + 72u);       // tile (1,1)
-                const double nf0 = wip_neg(f[0]), nf1 = wip_neg(f[1]);
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                             : "+d"(c0[0]), "+d"(c1[0]) : "d"(nf0), "d"(f[0]));
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                             : "+d"(c0[1]), "+d"(c1[1]) : "d"(nf1), "d"(f[0]));
-                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                             : "+d"(c0[2]), "+d"(c1[2]) : "d"(nf1), "d"(f[1]));
-                sts_f64_if(pd0, fr0, c0[0]);
-                sts_f64_if(pd1, fr0 + 8, c1[0]);
-                sts_f64(ra1, c0[1]);
-                sts_f64(ra1 + 8, c1[1]);
-                sts_f64_if(pd0, ra1 + 64u, c0[2]);
-                sts_f64_if(pd1, ra1 + 72u, c1[2]);
+#pragma unroll
+                for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj) {
+                        const unsigned ra = fr0 + 8u * (unsigned)(tri(8 * bi) + 8 * bi * r8) + 64u * bj;
+                        c0[bi * (bi + 1) / 2 + bj] = lds_f64(ra);
+                        c1[bi * (bi + 1) / 2 + bj] = lds_f64(ra + 8);
+                    }
+#pragma unroll
+                for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj) {
+                        const int t = bi * (bi + 1) / 2 + bj;
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                     : "+d"(c0[t]), "+d"(c1[t]) : "d"(wip_neg(f[bi])), "d"(f[bj]));
+                    }
+#pragma unroll
+                for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj) {
+                        const int t = bi * (bi + 1) / 2 + bj;
+                        const unsigned ra = fr0 + 8u * (unsigned)(tri(8 * bi) + 8 * bi * r8) + 64u * bj;
+                        if (bi == bj) {
+                            sts_f64_if(pd0, ra, c0[t]);
+                            sts_f64_if(pd1, ra + 8, c1[t]);
+                        } else {
+                            sts_f64(ra, c0[t]);
+                            sts_f64(ra + 8, c1[t]);
+                        }
+                    }
             }
             __syncwarp();
 #pragma unroll
@@ -222,7 +301,7 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         double ev = 0.0, g = 0.0;
         int pos = sub;
         bool fin = !has;
-        unsigned fmask = (n >= 16 ? 0u : (0xffffu << n)) & 0xffffu;   // finished rows of this matrix (bit = row)
+        unsigned fmask = (n >= G ? 0u : (0xffffffffu << n)) & ((1u << G) - 1u);   // finished rows of this matrix (bit = row)
         int cnt = 0, kstart = -1;
         bool win;
 
@@ -253,7 +332,7 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
             sts_f64_if(mine, prow + 8u * (unsigned)cnt, cs);
             fin = fin || (mine && lane == r);
             if (mine)
-                fmask |= 1u << (r & 15);
+                fmask |= 1u << (r & (G - 1));
         };
 
         // per-group algorithm state
@@ -262,11 +341,11 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         bool have_dmin = false;
         double lnext = 0.0;   // the last column's entry of L computed by a 2x2 tail
         // gamma / xi_diag = max |a_ii| folded from 0 (gmw81.rs:49-51, se90.rs:55-57, se99.rs:54-56)
-        gamma = seg_extreme<true>(grp, fabs(dg), has, 0.0);
+        gamma = seg_extreme<true, G>(grp, fabs(dg), has, 0.0);
         taugamma = dmul(MODCHOL_TAU, gamma);
         if constexpr (kAlgo == kGMW81) {
-            const unsigned ohi = seg_max_u32(grp, (unsigned)(om >> 32));
-            const unsigned olo = seg_max_u32(grp, (unsigned)(om >> 32) == ohi ? (unsigned)om : 0u);
+            const unsigned ohi = seg_max_u32<G>(grp, (unsigned)(om >> 32));
+            const unsigned olo = seg_max_u32<G>(grp, (unsigned)(om >> 32) == ohi ? (unsigned)om : 0u);
             const double off_max = __hiloint2double((int)ohi, (int)olo);
             const double nf = (double)n;
             delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(gamma, off_max)));
@@ -284,12 +363,12 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
                 const bool mine = phase == 0;
                 const int khi = __double2hiint(dg) & 0x7fffffff;
                 const unsigned klo = (unsigned)__double2loint(dg);
-                const int r = wipp_pivot_lane(grp, khi, klo, mine && !fin && dg == dg, fin, pos, j);   // gmw81.rs:71-78
+                const int r = wipp_pivot_lane<G>(grp, gbits, khi, klo, mine && !fin && dg == dg, fin, pos, j);   // gmw81.rs:71-78
                 take_position(mine, r, j);
-                const double col = column(r & 15);
+                const double col = column(r & (G - 1));
                 const double cjj = __shfl_sync(kFull, col, r);
                 const bool live = !fin && lane != r;
-                const double theta = seg_extreme<true>(grp, fabs(col), live, 0.0);   // gmw81.rs:87-100
+                const double theta = seg_extreme<true, G>(grp, fabs(col), live, 0.0);   // gmw81.rs:87-100
                 const double tb = dmul(theta, rbeta);
                 const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);        // gmw81.rs:102
                 double y = rsqrt_normal(dj);
@@ -308,13 +387,13 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
                     int khi;
                     unsigned klo;
                     wip_key(dg, khi, klo);
-                    const int r = wipp_pivot_lane(grp, khi, klo, mine && !fin && dg == dg, fin, pos, j);
+                    const int r = wipp_pivot_lane<G>(grp, gbits, khi, klo, mine && !fin && dg == dg, fin, pos, j);
                     const double piv = __shfl_sync(kFull, dg, r);
                     bool sw = false;
                     if (kAlgo == kSE99) {   // se99.rs:62-73, before the pivot is applied
                         double dmin = dmin_carry;
                         if (__any_sync(kFull, mine && !have_dmin)) {
-                            const double fresh = seg_extreme<false>(grp, dg, mine && !fin, INFINITY);
+                            const double fresh = seg_extreme<false, G>(grp, dg, mine && !fin, INFINITY);
                             dmin = have_dmin ? dmin_carry : fresh;
                         }
                         const double dmax = (piv == piv) ? piv : -INFINITY;
@@ -322,7 +401,7 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
                     }
                     const bool go = mine && !sw;   // this group applies its pivot
                     take_position(go, r, j);
-                    const double col = column(r & 15);
+                    const double col = column(r & (G - 1));
                     const bool live = go && !fin && lane != r;
                     const bool fast = fast_range_ok(piv);
                     const double y = rsqrt_normal(piv);
@@ -332,7 +411,7 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
                     double nv = dgn;   // look-ahead value (se90.rs:70-77, se99.rs:82-89)
                     if (!fast)
                         wip_slow_p1(piv, col, dg, sq, cs, dgn, nv);
-                    const double la = seg_extreme<false>(grp, nv, live, INFINITY);
+                    const double la = seg_extreme<false, G>(grp, nv, live, INFINITY);
                     const double thresh = (kAlgo == kSE99) ? dmul(-MODCHOL_MU, gamma) : taugamma;
                     const bool sw2 = go && la < thresh;   // the pivot at j stays applied (se99.rs:90-93)
                     const bool done = go && !sw2;         // column j is retired in phase 1
@@ -377,14 +456,14 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
                         int khi;   // se90.rs:115, se99.rs:135
                         unsigned klo;
                         wip_key(g, khi, klo);
-                        const int r = wipp_pivot_lane(grp, khi, klo, mine && !fin && g == g, fin, pos, j);
+                        const int r = wipp_pivot_lane<G>(grp, gbits, khi, klo, mine && !fin && g == g, fin, pos, j);
                         take_position(mine, r, j);
                         double piv = __shfl_sync(kFull, dg, r);
-                        const double col = column(r & 15);
+                        const double col = column(r & (G - 1));
                         const bool live = mine && !fin && lane != r;
                         const double acol = live ? abs_bits(col) : 0.0;
                         // E_jj (se90.rs:124-131, se99.rs:144-151)
-                        const double normj = wipp_sum16(acol);
+                        const double normj = wipp_sum<G>(acol);
                         const double ej = max_b_not_nan(dadd(-piv, max_b_not_nan(normj, taugamma)), delta_prev);
                         piv = dadd(piv, ej);
                         delta_prev = mine ? ej : delta_prev;
@@ -405,12 +484,12 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
                     } else if (j == n - 2) {
                         // final 2x2 block, never pivoted (se90.rs:155-166, se99.rs:175-186): the two rows
                         // alive sit at positions n-2 and n-1
-                        const unsigned bq0 = seg_ballot(grp, !fin && pos == n - 2);
-                        const unsigned bq1 = seg_ballot(grp, !fin && pos == n - 1);
-                        const int u0 = bq0 ? 31 - __clz(bq0) : 16 * grp, u1 = bq1 ? 31 - __clz(bq1) : 16 * grp;
+                        const unsigned bq0 = seg_ballot(gbits, !fin && pos == n - 2);
+                        const unsigned bq1 = seg_ballot(gbits, !fin && pos == n - 1);
+                        const int u0 = bq0 ? 31 - __clz(bq0) : G * grp, u1 = bq1 ? 31 - __clz(bq1) : G * grp;
                         double a00 = __shfl_sync(kFull, dg, u0);
                         double a11 = __shfl_sync(kFull, dg, u1);
-                        const double c2 = column(u0 & 15);
+                        const double c2 = column(u0 & (G - 1));
                         double a10 = __shfl_sync(kFull, c2, u1);
                         double lhi, llo;
                         eigenvalues_2x2(a00, a10, a10, a11, lhi, llo);   // lower storage: m[0,1] == m[1,0]
@@ -427,8 +506,8 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
                         lnext = mine ? (lane == u1 ? a11 : 0.0) : lnext;
                     } else {   // j == n - 1: the last entry of a 2x2 tail, or SE99's 1x1 tail (se99.rs:115-119)
                         const bool one = mine && kAlgo == kSE99 && kstart == n - 1;
-                        const unsigned ba = seg_ballot(grp, !fin);
-                        const int u = ba ? 31 - __clz(ba) : 16 * grp;
+                        const unsigned ba = seg_ballot(gbits, !fin);
+                        const int u = ba ? 31 - __clz(ba) : G * grp;
                         const double ljj = __shfl_sync(kFull, dg, u);
                         const double ej = tail1x1_e(ljj, gamma);
                         ev = (one && lane == u) ? ej : ev;
@@ -454,7 +533,7 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         {
             double* dstp = L ? L + (size_t)(gact ? b : b0) * nn + (size_t)pos * n : nullptr;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < NB; ++c) {
                 if (8 * c >= n)
                     break;
                 double v[8];

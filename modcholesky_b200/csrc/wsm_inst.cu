@@ -131,13 +131,14 @@ static cudaError_t launch_wip2(int n, long long batch, const double* a, double* 
     return cudaGetLastError();
 }
 
-// FAST mode, 8 < n <= 16, no fused solve: two matrices per warp (wipp_kernels.cuh)
-template <int kAlgo, int kN>
+// FAST mode, 4 < n <= 16, no fused solve: several matrices per warp (wipp_kernels.cuh)
+template <int kAlgo, int G, int kN>
 static cudaError_t launch_wipp(int n, long long batch, const double* a, double* l, double* e,
                                unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
-    auto kern = wipp_kernel<kAlgo, kN, 8>;
-    constexpr size_t smem = (size_t)kWipWarps * 2 * kWppMat * sizeof(double);
+    auto kern = wipp_kernel<kAlgo, G, kN, 8>;
+    constexpr int kGroups = 32 / G;
+    constexpr size_t smem = (size_t)kWipWarps * kGroups * wpp_mat_doubles(G) * sizeof(double);
     static int occ_dev[64];
     int dev = 0;
     cudaError_t ce = cudaGetDevice(&dev);
@@ -157,7 +158,7 @@ static cudaError_t launch_wipp(int n, long long batch, const double* a, double* 
         if (occ > 16) occ = 16;   // 64 warps per SM; 32 tensor-memory columns per block
         if (dev < 64) occ_dev[dev] = occ;
     }
-    long long blocks = (batch + kWipWarps * 2 - 1) / (kWipWarps * 2);
+    long long blocks = (batch + kWipWarps * kGroups - 1) / (kWipWarps * kGroups);
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
     kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
@@ -201,8 +202,11 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
     constexpr int A = MODCHOL_INST_ALGO;
     constexpr bool S = MODCHOL_INST_STRICT != 0;
     if (!S && x == nullptr && n > 8 && n <= 16 && wipp_enabled())
-        return n < 16 ? launch_wipp<A, 0>(n, batch, a, l, e, p, k, sms, st)
-                      : launch_wipp<A, 16>(n, batch, a, l, e, p, k, sms, st);
+        return n < 16 ? launch_wipp<A, 16, 0>(n, batch, a, l, e, p, k, sms, st)
+                      : launch_wipp<A, 16, 16>(n, batch, a, l, e, p, k, sms, st);
+    if (!S && x == nullptr && n > 4 && n <= 8 && wipp_enabled())
+        return n < 8 ? launch_wipp<A, 8, 0>(n, batch, a, l, e, p, k, sms, st)
+                     : launch_wipp<A, 8, 8>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 4)
         return launch_wsm<A, 4, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 8)
