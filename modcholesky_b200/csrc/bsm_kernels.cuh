@@ -185,6 +185,79 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// A -> working buffer by the bulk-copy engine (TMA): warp w stages storage row k (columns
+// c0 = (k+1) & ~1 .. n: the strict upper triangle, from an even column so that the copy is 16-byte
+// aligned) in its slot of the idle panel -- cp.async.bulk global -> shared, completion on the
+// warp's mbarrier --, takes the off-diagonal maximum from it (kMax, gmw81.rs:52-58) and sends it on
+// with cp.async.bulk shared -> global.  `slots` rows are in flight per block.  The extra element
+// copied when k + 1 is odd is the diagonal slot l[k n + k], which is written later anyway.
+template <bool kMax>
+__device__ __forceinline__ double bsm_copy_in_tma(const double* __restrict__ Ab, double* __restrict__ Lb, int n, int npad,
+                                                  unsigned pb, int slots, unsigned mbars, unsigned& tphase)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double om = 0.0;
+    if (warp < slots) {
+        const unsigned slot = pb + 8u * (unsigned)(warp * npad);
+        const unsigned mb = mbars + 8u * (unsigned)warp;
+        for (int k = warp; k < n - 1; k += slots) {
+            const int c0 = (k + 1) & ~1;
+            const unsigned bytes = 8u * (unsigned)(n - c0);
+            if (lane == 0) {
+                mbar_expect_tx(mb, bytes);
+                bulk_g2s(slot, Ab + (size_t)k * n + c0, bytes, mb);
+            }
+            mbar_wait(mb, tphase);
+            tphase ^= 1u;
+            if (kMax)
+                for (int i = k + 1 + lane; i < n; i += 32)
+                    om = fmax(om, fabs(lds_f64(slot + 8u * (unsigned)(i - c0))));
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(Lb + (size_t)k * n + c0, slot, bytes);
+                bulk_commit();
+                bulk_wait_read0();   // the slot may be overwritten
+            }
+            __syncwarp();
+        }
+        if (lane == 0)
+            bulk_wait0();            // written: the block's barrier that follows publishes it
+    }
+    return om;
+}
+
+// strict upper triangle := 0 by bulk stores of a zero line (the first n doubles of the panel)
+__device__ __forceinline__ void bsm_zero_upper_tma(double* __restrict__ Lb, int n, int npad, unsigned pb)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int q = threadIdx.x; q < npad; q += blockDim.x)
+        sts_f64(pb + 8u * (unsigned)q, 0.0);
+    fence_proxy_async();
+    __syncthreads();
+    if (lane == 0) {
+        for (int k = warp; k < n - 1; k += nwarps) {
+            int s0 = k + 1;
+            if (s0 & 1) {
+                Lb[(size_t)k * n + s0] = 0.0;
+                ++s0;
+            }
+            if (s0 < n)
+                bulk_s2g(Lb + (size_t)k * n + s0, pb, 8u * (unsigned)(n - s0));
+        }
+        bulk_commit();
+        bulk_wait_read0();   // the zero line may be overwritten (the stores complete on their own)
+    }
+}
+
 // Trailing update T(i,k) -= sum_c P(i,c) P(k,c) for j1 <= k < i < n, T(i,k) stored at Lb[k n + i],
 // and the same for the diagonal td[i] (shared memory).  Tile (bj, bi), bi >= bj, is held
 // transposed: fragment rows = k in block bj (A fragment: lane l holds P(8 bj + l/4, 4 h + l%4)),
@@ -295,9 +368,14 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
     const bool rv = row < n;
     // 128-bit tile accesses / bulk copies need 16-byte aligned rows
     const bool wide = (n & 1) == 0 && (((size_t)L) & 15) == 0;
-    if (tid == 0)
-        mbar_init(mbar, 1);
-    unsigned phase = 0;
+    // bulk copies (TMA) need 16-byte aligned rows of both buffers; one mbarrier per warp in the
+    // (otherwise unused) column line
+    const bool tma = wide && (((size_t)A) & 15) == 0;
+    const int slots = min(nwarps, (KB * ldp) / npad);
+    if (lane == 0)
+        mbar_init(lineb + 8u * (unsigned)(tid >> 5), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned tphase = 0;
     __syncthreads();
 
     for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
@@ -306,11 +384,15 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
         // ---- in: the strict upper triangle of A is T transposed; diagonal to shared memory;
         // off-diagonal maximum on the fly (gmw81.rs:52-58) ------------------------------------
         double om = 0.0;
-        for (int k = tid >> 5; k < n; k += nwarps) {   // one row per warp: coalesced
-            for (int i = k + 1 + lane; i < n; i += 32) {
-                const double v = __ldg(Ab + (size_t)k * n + i);
-                Lb[(size_t)k * n + i] = v;
-                om = fmax(om, fabs(v));
+        if (tma) {
+            om = bsm_copy_in_tma<true>(Ab, Lb, n, npad, pb, slots, lineb, tphase);
+        } else {
+            for (int k = tid >> 5; k < n; k += nwarps) {   // one row per warp: coalesced
+                for (int i = k + 1 + lane; i < n; i += 32) {
+                    const double v = __ldg(Ab + (size_t)k * n + i);
+                    Lb[(size_t)k * n + i] = v;
+                    om = fmax(om, fabs(v));
+                }
             }
         }
         double cd = rv ? __ldg(Ab + (size_t)row * (n + 1)) : 0.0;   // running diagonal (gmw81.rs:66-67)
@@ -463,9 +545,13 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
         }
 
         // ---- out: strict upper triangle zero (gmw81.rs:112-125), e un-permuted, p ---------------
-        for (int k = tid >> 5; k < n; k += nwarps)
-            for (int i = k + 1 + lane; i < n; i += 32)
-                Lb[(size_t)k * n + i] = 0.0;
+        if (tma) {
+            bsm_zero_upper_tma(Lb, n, npad, pb);
+        } else {
+            for (int k = tid >> 5; k < n; k += nwarps)
+                for (int i = k + 1 + lane; i < n; i += 32)
+                    Lb[(size_t)k * n + i] = 0.0;
+        }
         if (rv) {
             E[(size_t)b * n + perm] = ev;                               // gmw81.rs:127-131
             P[(size_t)b * n + row] = (unsigned long long)perm;
@@ -474,6 +560,8 @@ bsm_gmw_kernel(int n, long long batch, const double* __restrict__ A, double* __r
             K[b] = -1;
         __syncthreads();
     }
+    if (tma && lane == 0)
+        bulk_wait0();   // the last matrix's zero-fill
 }
 
 
@@ -504,14 +592,25 @@ bsm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
     const int row = tid;
     const bool rv = row < n;
     const bool wide = (n & 1) == 0 && (((size_t)L) & 15) == 0;
+    const bool tma = wide && (((size_t)A) & 15) == 0;   // see bsm_gmw_kernel
+    const int slots = min(nwarps, (KB * ldp) / npad);
+    if (lane == 0)
+        mbar_init(lineb + 8u * (unsigned)(tid >> 5), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned tphase = 0;
+    __syncthreads();
 
     for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
         const double* Ab = A + (size_t)b * nn;
         double* Lb = L + (size_t)b * nn;
         // ---- in: the strict upper triangle of A is T transposed; diagonal to registers -----------
-        for (int k = tid >> 5; k < n; k += nwarps)
-            for (int i = k + 1 + lane; i < n; i += 32)
-                Lb[(size_t)k * n + i] = __ldg(Ab + (size_t)k * n + i);
+        if (tma) {
+            bsm_copy_in_tma<false>(Ab, Lb, n, npad, pb, slots, lineb, tphase);
+        } else {
+            for (int k = tid >> 5; k < n; k += nwarps)
+                for (int i = k + 1 + lane; i < n; i += 32)
+                    Lb[(size_t)k * n + i] = __ldg(Ab + (size_t)k * n + i);
+        }
         double cd = rv ? __ldg(Ab + (size_t)row * (n + 1)) : 0.0;   // running diagonal
         if (row < npad)
             sts_f64(tdb + 8u * (unsigned)row, cd);
@@ -779,9 +878,13 @@ bsm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
         __syncthreads();
 
         // ---- out: strict upper triangle zero (se99.rs:189-192), e un-permuted (se99.rs:194-198), p
-        for (int k = tid >> 5; k < n; k += nwarps)
-            for (int i = k + 1 + lane; i < n; i += 32)
-                Lb[(size_t)k * n + i] = 0.0;
+        if (tma) {
+            bsm_zero_upper_tma(Lb, n, npad, pb);
+        } else {
+            for (int k = tid >> 5; k < n; k += nwarps)
+                for (int i = k + 1 + lane; i < n; i += 32)
+                    Lb[(size_t)k * n + i] = 0.0;
+        }
         if (rv) {
             E[(size_t)b * n + perm] = ev;
             P[(size_t)b * n + row] = (unsigned long long)perm;
@@ -790,6 +893,8 @@ bsm_se_kernel(int n, long long batch, const double* __restrict__ A, double* __re
             K[b] = kstart;
         __syncthreads();
     }
+    if (tma && lane == 0)
+        bulk_wait0();   // the last matrix's zero-fill
 }
 
 }  // namespace modchol

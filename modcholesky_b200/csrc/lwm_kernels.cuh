@@ -42,14 +42,6 @@ __host__ __device__ inline size_t lwm_smem_bytes(int n, int kb)
     return 8 * ((size_t)kb * bsm_ldp(n) + 5 * npad + 2 * 8 * kLwmStageLd + 2) + 4 * npad;
 }
 
-__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y)
 {
     smem_check(a, 16u);
