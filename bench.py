@@ -495,6 +495,16 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "matrices/s", "cores": cores, "kind": "port",
                                 "sample": f"{sub.shape[0]} of the {batch} matrices, {secs:.1f} s wall on "
                                           f"{cores} threads (C restatement of the reference; Rust absent)"}
+    # the thread-per-device host entry point (modchol_factor_batched_multi_gpu_f64) on every GPU of the
+    # job: rank 0, host buffers, untimed, checked against the single-device result
+    if world > 1:
+        if rank == 0:
+            sub = a[:4096].cpu().numpy()
+            d1 = m.factor_batched(ALGO, sub, mode="strict")
+            dn = m.factor_batched(ALGO, sub, mode="strict", ngpus=world)
+            line["multi_gpu_entry_check"] = bool(np.array_equal(d1.l, dn.l) and np.array_equal(d1.e, dn.e)
+                                                 and np.array_equal(d1.p, dn.p))
+        dist.barrier()
     if rank == 0 and world == 1 and not args.no_configs:
         del a
         torch.cuda.empty_cache()
