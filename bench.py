@@ -130,13 +130,24 @@ def ncu_traffic():
 
 
 def kernel_name(m, algo, n, mode):
+    """Kernel class reported by the library plus the kernel the dispatcher runs for it."""
     cls = m.kernel_class(algo, n, mode)
-    if mode == "fast" and cls == "warp_smem" and 12 < n <= 32 and os.environ.get("MODCHOL_WIP", "1") != "0":
-        return f"{cls}: wip_kernel<{algo.upper()}, n={n}> (implicit pivoting, L in tensor memory, DMMA updates)"
-    names = {"warp_smem": "wsm_se_kernel / wsm_gmw_kernel", "cta_packed": "csm_*_kernel",
-             "cta_blocked": "bsm_gmw_kernel", "cta_smem": "*_cta_kernel", "cta_gmem": "*_cta_kernel",
-             "warp32": "warp_*_kernel"}
-    return f"{cls}: {names.get(cls, cls)}<{algo.upper()}, {mode}>"
+    A = algo.upper()
+    if mode == "fast" and cls == "warp_smem" and n > 4:
+        if n <= 8:
+            return f"{cls}: wipp_kernel<{A}, G=8> (implicit pivoting, four matrices per warp, L in tensor memory)"
+        if n <= 16:
+            return f"{cls}: wipp_kernel<{A}, G=16> (implicit pivoting, two matrices per warp, L in tensor memory)"
+        if n <= 32:
+            return f"{cls}: wip_kernel<{A}, n={n}> (implicit pivoting, L in tensor memory, DMMA rank-8 updates)"
+        return f"{cls}: wip2_kernel<{A}> (implicit pivoting, two rows per lane, L in tensor memory, DMMA updates)"
+    if cls == "cta_blocked":
+        return f"{cls}: {'bsm_gmw_kernel' if algo == 'gmw81' else 'bsm_se_kernel'}<{A}> (panel in shared memory, DMMA trailing update from L2)"
+    names = {"warp_smem": "wsm_gmw_kernel" if algo == "gmw81" else "wsm_se_kernel",
+             "cta_packed": "csm_gmw_kernel" if algo == "gmw81" else "csm_se_kernel",
+             "cta_smem": "gmw81_cta_kernel" if algo == "gmw81" else "se_cta_kernel",
+             "cta_gmem": "gmw81_cta_kernel" if algo == "gmw81" else "se_cta_kernel", "warp32": "warp_*_kernel"}
+    return f"{cls}: {names.get(cls, cls)}<{A}, {mode}>"
 
 
 def time_steps(torch, fn, steps, warmup):
