@@ -204,6 +204,21 @@ def other_configs(torch, np, m, dev, peak):
         if key == "configs[1]":
             vms = time_steps(torch, lambda: m.verify_batched(a, d), 3, 1)
             ent["verify_ms"] = vms
+            # the other kernels either side of the path, on the same batch, against the HBM roofline
+            gms = time_steps(torch, lambda: m.gershgorin_circles_batched(a), 3, 1)
+            gb = batch * (8 * n * n + 16 * n) / (gms * 1e-3) / 1e9
+            vb = batch * (16 * n * n + 16 * n + 12) / (vms * 1e-3) / 1e9
+            rhs = torch.ones((batch, n), dtype=torch.float64, device=dev)
+            sms_ = time_steps(torch, lambda: m.solve_batched(d, rhs), 3, 1)
+            sb = batch * (8 * n * n + 24 * n) / (sms_ * 1e-3) / 1e9
+            ent["aux_kernels"] = {
+                "gershgorin_circles": {"ms": gms, "GBps": gb, "frac_of_hbm_peak": gb / peak,
+                                       "algorithmic_bytes_per_matrix": 8 * n * n + 16 * n},
+                "verify": {"ms": vms, "GBps": vb, "frac_of_hbm_peak": vb / peak,
+                           "algorithmic_bytes_per_matrix": 16 * n * n + 16 * n + 12},
+                "solve": {"ms": sms_, "GBps": sb, "frac_of_hbm_peak": sb / peak,
+                          "algorithmic_bytes_per_matrix": 8 * n * n + 24 * n}}
+            del rhs
         out[key] = ent
         del a, d, resid, flags
         torch.cuda.empty_cache()
