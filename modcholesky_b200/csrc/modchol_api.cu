@@ -17,6 +17,8 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "launch_cache.cuh"
+#include "wsm_se.cuh"
 #include "common.cuh"
 #include "cta_kernels.cuh"
 #include "warp_kernels.cuh"
@@ -24,6 +26,9 @@
 namespace {
 
 using namespace modchol;
+
+cudaError_t launch_solve(long long batch, int n, int nrhs, const double* l, const unsigned long long* p,
+                         const double* b, double* x, int sms, cudaStream_t st);
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
@@ -97,6 +102,16 @@ int ctx_init(int dev)
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(4 * MODCHOL_MAX_N * sizeof(double)));
+        // stream-ordered scratch (factor_solve_device, the spill buffers of the large-n kernels)
+        // stays in the device's pool between calls instead of going back to the driver at every
+        // synchronisation
+        if (e == cudaSuccess) {
+            cudaMemPool_t pool = nullptr;
+            unsigned long long keep = (unsigned long long)1 << 30;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaGetLastError();
+        }
         c.init_rc = (int)e;
     });
     if (c.init_rc != 0)
@@ -487,9 +502,10 @@ int check_common(int algo, int mode, long long batch, int n, const void* a, cons
     return MODCHOL_OK;
 }
 
-// Factorise and solve with device pointers.  n <= 64 (shared-memory warp kernels): ONE kernel, the
-// factor never leaves shared memory unless l is asked for.  Otherwise: factor kernel into l / p
-// (stream-ordered scratch when the caller passes NULL), then the batched solve kernel.
+// Factorise and solve with device pointers.  STRICT n <= 64 and FAST n <= 4 (shared-memory warp
+// kernels): ONE kernel, the factor never leaves shared memory unless l is asked for.  Otherwise:
+// factor kernel into l / p (stream-ordered scratch when the caller passes NULL), then the batched
+// solve kernel.
 int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int nrhs,
                         const double* a, const double* b, double* x, double* l, double* e,
                         unsigned long long* p, int* k, cudaStream_t st)
@@ -500,31 +516,43 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
     if (rc)
         return rc;
     const DeviceCtx& c = g_ctx[dev];
-    if (classify(algo, mode, n, c.smem_optin) == kClsWarpSmem) {
+    // FAST, 4 < n <= 64: the implicit-pivoting factor kernels (no fused solve) followed by the
+    // shared-memory solve kernel beat the fused position-ordered kernel although L makes a round
+    // trip through HBM (n = 32: 107 against 84 M systems/s, n = 16: 338 against 279)
+    const bool fused = classify(algo, mode, n, c.smem_optin) == kClsWarpSmem &&
+                       !(mode == MODCHOL_MODE_FAST && n > 4 && getenv("MODCHOL_WIPP") == nullptr);
+    if (fused) {
         cudaError_t ce = launch_wsm_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st, b, x, nrhs);
         g_launches.fetch_add(1);
         if (ce != cudaSuccess)
             return fail(MODCHOL_ERR_CUDA, "fused factor+solve launch failed: %s", cudaGetErrorString(ce));
         return MODCHOL_OK;
     }
+    // Scratch for the outputs the caller did not ask for is stream-ordered and bounded: the batch
+    // runs in chunks of at most kScratchBytes of L, so a call with l == NULL costs 512 MB of pool
+    // memory whatever the batch (the pool keeps it between calls: ctx_init raises its release
+    // threshold), and each chunk's factor and solve kernels follow each other on the stream.
     const size_t nn = (size_t)n * n;
+    constexpr size_t kScratchBytes = (size_t)512 << 20;
+    long long chunk = batch;
+    if (!l)
+        chunk = std::min<long long>(batch, std::max<long long>(1, (long long)(kScratchBytes / (nn * sizeof(double)))));
     double *lt = nullptr, *et = nullptr;
     unsigned long long* pt = nullptr;
     cudaError_t ce = cudaSuccess;
-    if (!l) ce = cudaMallocAsync(&lt, (size_t)batch * nn * sizeof(double), st);
-    if (ce == cudaSuccess && !e) ce = cudaMallocAsync(&et, (size_t)batch * n * sizeof(double), st);
-    if (ce == cudaSuccess && !p) ce = cudaMallocAsync(&pt, (size_t)batch * n * sizeof(unsigned long long), st);
-    if (ce == cudaSuccess) {
-        double* lw = l ? l : lt;
-        unsigned long long* pw = p ? p : pt;
-        rc = factor_device(dev, algo, mode, batch, n, a, lw, e ? e : et, pw, k, st);
+    if (!l) ce = cudaMallocAsync(&lt, (size_t)chunk * nn * sizeof(double), st);
+    if (ce == cudaSuccess && !e) ce = cudaMallocAsync(&et, (size_t)chunk * n * sizeof(double), st);
+    if (ce == cudaSuccess && !p) ce = cudaMallocAsync(&pt, (size_t)chunk * n * sizeof(unsigned long long), st);
+    for (long long c0 = 0; ce == cudaSuccess && rc == MODCHOL_OK && c0 < batch; c0 += chunk) {
+        const long long cb = std::min(chunk, batch - c0);
+        double* lw = l ? l + (size_t)c0 * nn : lt;
+        double* ew = e ? e + (size_t)c0 * n : et;
+        unsigned long long* pw = p ? p + (size_t)c0 * n : pt;
+        rc = factor_device(dev, algo, mode, cb, n, a + (size_t)c0 * nn, lw, ew, pw, k ? k + c0 : nullptr, st);
         if (rc == MODCHOL_OK) {
-            const size_t smem = (size_t)4 * n * sizeof(double);
-            const long long total = batch * (long long)nrhs;
-            const unsigned grid = (unsigned)std::min<long long>((total + 3) / 4, (long long)c.sms * 16);
-            solve_kernel<<<grid, 128, smem, st>>>(batch, n, nrhs, lw, pw, b, x);
+            const size_t off = (size_t)c0 * nrhs * n;
+            ce = launch_solve(cb, n, nrhs, lw, pw, b + off, x + off, c.sms, st);
             g_launches.fetch_add(1);
-            ce = cudaGetLastError();
         }
     }
     if (lt) cudaFreeAsync(lt, st);
@@ -535,6 +563,79 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
     if (ce != cudaSuccess)
         return fail(MODCHOL_ERR_CUDA, "factor+solve: %s", cudaGetErrorString(ce));
     return MODCHOL_OK;
+}
+
+// Batched solve for n <= 64: the lower triangle of L is staged once in shared memory (packed, 32/G
+// matrices per warp as in wsm_se.cuh) and every right-hand side runs the substitution of the fused
+// kernel (wsm_solve_in_place: forward over the columns of L, backward over its rows, one broadcast
+// + one LDS + one FMA per row and step) -- no shuffle reduction and no division inside a step.
+template <int G, int R>
+__global__ void __launch_bounds__(128)
+solve_warp_kernel(int n, int wstride, long long batch, int nrhs, const double* __restrict__ L,
+                  const unsigned long long* __restrict__ P, const double* B, double* X)   // X may alias B
+{
+    extern __shared__ double sm[];
+    constexpr int kPack = 32 / G, kWarps = 4;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane & (G - 1), grp = lane / G;
+    const unsigned mask = wsm_group_mask<G>(grp);
+    const unsigned wb = (unsigned)__cvta_generic_to_shared(sm + (size_t)(wib * kPack + grp) * wstride);
+    int row[R], perm[R];
+    unsigned tib[R];
+    bool rv[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        row[s] = sub + G * s;
+        rv[s] = row[s] < n;
+        tib[s] = wb + 8u * (unsigned)tri(rv[s] ? row[s] : 0);
+    }
+    const size_t nn = (size_t)n * n;
+    const long long nslots = (long long)gridDim.x * kWarps * kPack;
+    for (long long b = ((long long)blockIdx.x * kWarps + wib) * kPack + grp; b < batch; b += nslots) {
+        __syncwarp(mask);
+        wsm_load_lower<G, R, false>(L + (size_t)b * nn, n, wb, sub);
+        __syncwarp(mask);
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            perm[s] = rv[s] ? (int)P[(size_t)b * n + row[s]] : 0;
+        wsm_solve_in_place<G, R>(mask, n, wb, tib, row, rv, perm, B + (size_t)b * nrhs * n,
+                                 X + (size_t)b * nrhs * n, nrhs);
+    }
+}
+
+template <int G, int R>
+cudaError_t launch_solve_warp(int n, long long batch, int nrhs, const double* l, const unsigned long long* p,
+                              const double* b, double* x, int sms, cudaStream_t st)
+{
+    auto kern = solve_warp_kernel<G, R>;
+    constexpr int kPack = 32 / G;
+    const int wstride = wsm_warp_doubles(n);
+    const size_t smem = (size_t)4 * kPack * wstride * sizeof(double);
+    const size_t smem_max = (size_t)4 * kPack * wsm_warp_doubles(G * R) * sizeof(double);
+    int occ = 1;
+    cudaError_t ce = cached_occupancy(kern, 128, smem, smem_max, &occ);
+    if (ce != cudaSuccess) return ce;
+    long long blocks = (batch + 4 * kPack - 1) / (4 * kPack);
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;
+    kern<<<(unsigned)blocks, 128, smem, st>>>(n, wstride, batch, nrhs, l, p, b, x);
+    return cudaGetLastError();
+}
+
+// n <= 64: the shared-memory warp kernel; larger n: one warp per system on rows of L in global memory
+cudaError_t launch_solve(long long batch, int n, int nrhs, const double* l, const unsigned long long* p,
+                         const double* b, double* x, int sms, cudaStream_t st)
+{
+    if (n <= 4) return launch_solve_warp<4, 1>(n, batch, nrhs, l, p, b, x, sms, st);
+    if (n <= 8) return launch_solve_warp<8, 1>(n, batch, nrhs, l, p, b, x, sms, st);
+    if (n <= 16) return launch_solve_warp<16, 1>(n, batch, nrhs, l, p, b, x, sms, st);
+    if (n <= 32) return launch_solve_warp<32, 1>(n, batch, nrhs, l, p, b, x, sms, st);
+    if (n <= 64) return launch_solve_warp<32, 2>(n, batch, nrhs, l, p, b, x, sms, st);
+    const size_t smem = (size_t)4 * n * sizeof(double);
+    const long long total = batch * (long long)nrhs;
+    const unsigned grid = (unsigned)std::min<long long>((total + 3) / 4, (long long)sms * 16);
+    solve_kernel<<<grid, 128, smem, st>>>(batch, n, nrhs, l, p, b, x);
+    return cudaGetLastError();
 }
 
 // n <= 64: one warp per matrix, L L^T on the FP64 tensor pipe; larger n: one CTA per matrix
@@ -816,9 +917,9 @@ int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const doub
             // another lane only within one system, and each system is staged in shared memory
             // before any write -- aliasing is safe.
         }
-        solve_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(batch, n, nrhs, l, pu, b, x);
+        const cudaError_t ce = launch_solve(batch, n, nrhs, l, pu, b, x, g_ctx[dev].sms, static_cast<cudaStream_t>(stream));
         g_launches.fetch_add(1);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(ce);
         return MODCHOL_OK;
     }
     if (mem_kind != MODCHOL_MEM_HOST)
@@ -833,9 +934,8 @@ int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const doub
     if (ce == cudaSuccess) ce = cudaMemcpy(dp, p, (size_t)batch * n * 8, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = cudaMemcpy(db, b, (size_t)total * n * 8, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) {
-        solve_kernel<<<grid, 128, smem>>>(batch, n, nrhs, dl, dp, db, db);
+        ce = launch_solve(batch, n, nrhs, dl, dp, db, db, g_ctx[dev].sms, nullptr);
         g_launches.fetch_add(1);
-        ce = cudaGetLastError();
     }
     if (ce == cudaSuccess) ce = cudaMemcpy(x, db, (size_t)total * n * 8, cudaMemcpyDeviceToHost);
     cudaFree(dl); cudaFree(dp); cudaFree(db);

@@ -42,6 +42,9 @@ namespace modchol {
 
 constexpr int kWipTri = 528;       // T(32) doubles of packed triangle
 constexpr int kWipPanelLd = 36;    // panel column stride: == 4 (mod 16) doubles, see above
+#ifndef MODCHOL_WIP_TWOCHAIN
+#define MODCHOL_WIP_TWOCHAIN 0   /* pending-column corrections as two FMA chains (1) or one (0) */
+#endif
 #ifndef MODCHOL_WIP_KB
 #define MODCHOL_WIP_KB 8
 #endif
@@ -121,10 +124,17 @@ __device__ __forceinline__ double wip_sum32(double x)
     const double one = 1.0, zero = 0.0;
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %4};"
                  : "=d"(q0), "=d"(q1) : "d"(one), "d"(x), "d"(zero));
-    const double h = dadd(q0, q1);
+    double h = dadd(q0, q1);
+#if MODCHOL_WIP_DMMA_SUM == 2
+    // the four lanes of a quad hold the pairwise sums of the eight quad sums: two shuffle rounds
+    h = dadd(h, __shfl_xor_sync(kFull, h, 1));
+    h = dadd(h, __shfl_xor_sync(kFull, h, 2));
+    return h;
+#else
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %4};"
                  : "=d"(s0), "=d"(s1) : "d"(h), "d"(one), "d"(zero));
     return s0;
+#endif
 }
 
 // pivots outside the safe range of the rsqrt formulas (<= 0, NaN, Inf, subnormal, huge): the
@@ -444,10 +454,19 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                     col = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col);
                 return col;
             } else {
+#if MODCHOL_WIP_TWOCHAIN
+            double col2 = 0.0;   // odd pending columns: a second, independent chain
+#endif
             auto corr = [&](auto ctag) {
                 constexpr int c = decltype(ctag)::value;
-                if constexpr (c < kWipKB - 1)
+                if constexpr (c < kWipKB - 1) {
+#if MODCHOL_WIP_TWOCHAIN
+                    if constexpr (c % 2 == 1)
+                        col2 = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col2);
+                    else
+#endif
                     col = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col);
+                }
             };
             // a tree of warp-uniform branches on the count (no jump table: its constant load and
             // indirect branch sat on the step's critical path twice)
@@ -467,6 +486,10 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
             } else if (C == 1) {
                 corr(IC<0>{});
             }
+#if MODCHOL_WIP_TWOCHAIN
+            if (C >= 2)
+                col = dadd(col, col2);
+#endif
             return col;
             }
         };
