@@ -502,8 +502,8 @@ int check_common(int algo, int mode, long long batch, int n, const void* a, cons
     return MODCHOL_OK;
 }
 
-// Factorise and solve with device pointers.  STRICT n <= 64 and FAST n <= 4 (shared-memory warp
-// kernels): ONE kernel, the factor never leaves shared memory unless l is asked for.  Otherwise:
+// Factorise and solve with device pointers.  n <= 64 (shared-memory warp kernels): ONE kernel,
+// the factor never leaves the SM unless l is asked for.  Otherwise:
 // factor kernel into l / p (stream-ordered scratch when the caller passes NULL), then the batched
 // solve kernel.
 int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int nrhs,
@@ -516,11 +516,8 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
     if (rc)
         return rc;
     const DeviceCtx& c = g_ctx[dev];
-    // FAST, 4 < n <= 64: the implicit-pivoting factor kernels (no fused solve) followed by the
-    // shared-memory solve kernel beat the fused position-ordered kernel although L makes a round
-    // trip through HBM (n = 32: 107 against 84 M systems/s, n = 16: 338 against 279)
-    const bool fused = classify(algo, mode, n, c.smem_optin) == kClsWarpSmem &&
-                       !(mode == MODCHOL_MODE_FAST && n > 4 && getenv("MODCHOL_WIPP") == nullptr);
+    // every shared-memory warp class (n <= 64, both modes) carries its own fused solve
+    const bool fused = classify(algo, mode, n, c.smem_optin) == kClsWarpSmem;
     if (fused) {
         cudaError_t ce = launch_wsm_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st, b, x, nrhs);
         g_launches.fetch_add(1);

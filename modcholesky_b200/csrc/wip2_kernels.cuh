@@ -26,10 +26,12 @@ constexpr int kWip2Ld = 68;          // panel column stride: >= 64, == 4 (mod 16
 constexpr int kWip2Doubles = kWip2Tri + kWipKB * kWip2Ld;
 constexpr int kWip2TmemCols = 256;   // two rows of 64 doubles per lane
 
-template <int kAlgo, int NB, int kN, int kMinBlocks>
+// kSolve: fused consumer step, as in wip_kernel (two positions per lane in the substitution).
+template <int kAlgo, int NB, int kN, int kMinBlocks, bool kSolve = false>
 __global__ void __launch_bounds__(kWipWarps * 32, kMinBlocks)
 wip2_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __restrict__ L,
-            double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+            double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
+            const double* Bm = nullptr, double* X = nullptr, int nrhs = 0)
 {
     extern __shared__ double sm[];
     __shared__ unsigned tmem_base;
@@ -512,25 +514,34 @@ wip2_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         // ---- epilogue: the two rows of L leave tensor memory for rows pos0 / pos1 of the output;
         // e in original order (se99.rs:194-198); p -------------------------------------------------
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (L) {
+        if constexpr (kSolve)
+            __syncwarp();   // every lane is done reading C from the triangle
+        if (L || kSolve) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const bool has = s ? has1 : has0;
-                double* dstp = L + (size_t)b * nn + (size_t)(s ? pos1 : pos0) * n;
+                const int ps = s ? pos1 : pos0;
+                double* dstp = L + (size_t)b * nn + (size_t)ps * n;
+                const unsigned rowb = wb + 8u * (unsigned)tri(ps);   // row ps of the position-ordered triangle
 #pragma unroll
                 for (int c = 0; c < NB; ++c) {
                     if (8 * c >= n)
                         break;
                     double v[8];
                     wip_tmem_load8(tw + 128u * s + 16u * c, v);
-                    if (wide && has) {
+                    if (L && wide && has) {
                         stg_v4f64(dstp + 8 * c, v[0], v[1], v[2], v[3]);
                         stg_v4f64(dstp + 8 * c + 4, v[4], v[5], v[6], v[7]);
-                    } else if (!wide && has) {
+                    } else if (L && !wide && has) {
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
                             if (8 * c + u < n)
                                 dstp[8 * c + u] = v[u];
+                    }
+                    if constexpr (kSolve) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            sts_f64_if(has && 8 * c + u <= ps, rowb + 8u * (unsigned)(8 * c + u), v[u]);
                     }
                 }
             }
@@ -545,6 +556,19 @@ wip2_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         }
         if (K && lane == 0)
             K[b] = kstart;
+        if constexpr (kSolve) {
+            // lane -> positions lane, lane + 32 through the (now free) panel area, then the
+            // substitutions on the position-ordered triangle
+            sts_f64(pnb + 8u * (unsigned)pos0, (double)lane);
+            sts_f64(pnb + 8u * (unsigned)pos1, (double)(lane + 32));
+            __syncwarp();
+            const unsigned tibs[2] = {tib0, tib1};
+            const int rows[2] = {lane, lane + 32};
+            const bool rvs[2] = {has0, has1};
+            const int perms[2] = {(int)lds_f64(pnb + 8u * (unsigned)lane), (int)lds_f64(pnb + 8u * (unsigned)(lane + 32))};
+            wsm_solve_in_place<32, 2>(kFull, n, wb, tibs, rows, rvs, perms, Bm + (size_t)b * nrhs * n,
+                                      X + (size_t)b * nrhs * n, nrhs);
+        }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

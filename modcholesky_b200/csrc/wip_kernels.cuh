@@ -35,16 +35,13 @@
 #include "wsm_se.cuh"
 
 #ifndef MODCHOL_WIP_DMMA_SUM
-#define MODCHOL_WIP_DMMA_SUM 1   /* column norm: two DMMAs (1) or five shuffle rounds (0) */
+#define MODCHOL_WIP_DMMA_SUM 1   /* column norm: two DMMAs (1), one DMMA + two shuffle rounds (2) or five shuffle rounds (0) */
 #endif
 
 namespace modchol {
 
 constexpr int kWipTri = 528;       // T(32) doubles of packed triangle
 constexpr int kWipPanelLd = 36;    // panel column stride: == 4 (mod 16) doubles, see above
-#ifndef MODCHOL_WIP_TWOCHAIN
-#define MODCHOL_WIP_TWOCHAIN 0   /* pending-column corrections as two FMA chains (1) or one (0) */
-#endif
 #ifndef MODCHOL_WIP_KB
 #define MODCHOL_WIP_KB 8
 #endif
@@ -190,10 +187,16 @@ __device__ __forceinline__ void stg_v4f64(double* p, double a, double b, double 
 // kN: compile-time n (0: run-time n <= 8 NB).  kRegC: C fragments resident in registers (40 per
 // lane, 20 warps per SM) or in the shared-memory triangle only (one LDS/DMMA/STS round trip per
 // tile and update, 64 registers, 32 warps per SM).
-template <int kAlgo, int NB, int kN, bool kRegC, int kMinBlocks>
+// kSolve: the consumer step (A + E) x = rhs fused behind the factorisation (Bm, X: batch x nrhs x n,
+// X may alias Bm): the epilogue also lays the rows of L down in the shared-memory triangle in
+// POSITION order (row pos of lane i at T(pos)), the lanes change role (lane = position) and run
+// the substitutions of wsm_solve_in_place on it -- L does not make the round trip through HBM, and
+// is not written at all when the caller passes L == NULL.
+template <int kAlgo, int NB, int kN, bool kRegC, int kMinBlocks, bool kSolve = false>
 __global__ void __launch_bounds__(kWipWarps * 32, kMinBlocks)
 wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __restrict__ L,
-           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
+           const double* Bm = nullptr, double* X = nullptr, int nrhs = 0)
 {
     extern __shared__ double sm[];
     __shared__ unsigned tmem_base;
@@ -454,19 +457,10 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                     col = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col);
                 return col;
             } else {
-#if MODCHOL_WIP_TWOCHAIN
-            double col2 = 0.0;   // odd pending columns: a second, independent chain
-#endif
             auto corr = [&](auto ctag) {
                 constexpr int c = decltype(ctag)::value;
-                if constexpr (c < kWipKB - 1) {
-#if MODCHOL_WIP_TWOCHAIN
-                    if constexpr (c % 2 == 1)
-                        col2 = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col2);
-                    else
-#endif
+                if constexpr (c < kWipKB - 1)
                     col = __fma_rn(-csr[c], lds_f64(pr + 8u * (unsigned)(kWipPanelLd * c)), col);
-                }
             };
             // a tree of warp-uniform branches on the count (no jump table: its constant load and
             // indirect branch sat on the step's critical path twice)
@@ -486,10 +480,6 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
             } else if (C == 1) {
                 corr(IC<0>{});
             }
-#if MODCHOL_WIP_TWOCHAIN
-            if (C >= 2)
-                col = dadd(col, col2);
-#endif
             return col;
             }
         };
@@ -767,8 +757,11 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
         // ---- epilogue: this lane's row of L leaves tensor memory for row `pos` of the output,
         // zero beyond the diagonal (se99.rs:189-192); e in original order (se99.rs:194-198); p ---
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (L) {
+        if constexpr (kSolve)
+            __syncwarp();   // every lane is done reading C from the triangle
+        if (L || kSolve) {
             double* dstp = L + (size_t)b * nn + (size_t)pos * n;
+            const unsigned rowb = wb + 8u * (unsigned)tri(pos);   // row pos of the position-ordered triangle
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 if (8 * c >= n)
@@ -776,14 +769,19 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
                 double v[8];
                 wip_tmem_load8(tw + 16u * c, v);
                 // (entries beyond the diagonal were stored as zeros: a finished row receives 0)
-                if (wide && has) {
+                if (L && wide && has) {
                     stg_v4f64(dstp + 8 * c, v[0], v[1], v[2], v[3]);
                     stg_v4f64(dstp + 8 * c + 4, v[4], v[5], v[6], v[7]);
-                } else if (!wide && has) {
+                } else if (L && !wide && has) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (8 * c + u < n)
                             dstp[8 * c + u] = v[u];
+                }
+                if constexpr (kSolve) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        sts_f64_if(has && 8 * c + u <= pos, rowb + 8u * (unsigned)(8 * c + u), v[u]);
                 }
             }
         }
@@ -795,6 +793,18 @@ wip_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __re
         }
         if (K && lane == 0)
             K[b] = kstart;
+        if constexpr (kSolve) {
+            // lane -> position: the original index sitting at position `lane` through the panel
+            // area (free now), then L z = P rhs, L^T w = z, x[p_i] = w_i on the triangle
+            sts_f64(pnb + 8u * (unsigned)pos, (double)lane);
+            __syncwarp();
+            const unsigned tibs[1] = {tib};
+            const int rows[1] = {lane};
+            const bool rvs[1] = {has};
+            const int perms[1] = {(int)lds_f64(pnb + 8u * (unsigned)lane)};
+            wsm_solve_in_place<32, 1>(kFull, n, wb, tibs, rows, rvs, perms, Bm + (size_t)b * nrhs * n,
+                                      X + (size_t)b * nrhs * n, nrhs);
+        }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -137,10 +137,13 @@ __device__ __forceinline__ double wipp_sum(double x)
     return x;
 }
 
-template <int kAlgo, int G, int kN, int kMinBlocks>
+// kSolve: fused consumer step, as in wip_kernel (every group solves its own systems; the
+// substitution's broadcasts are shuffles of width G under the full member mask).
+template <int kAlgo, int G, int kN, int kMinBlocks, bool kSolve = false>
 __global__ void __launch_bounds__(kWipWarps * 32, kMinBlocks)
 wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __restrict__ L,
-            double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+            double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
+            const double* Bm = nullptr, double* X = nullptr, int nrhs = 0)
 {
     extern __shared__ double sm[];
     __shared__ unsigned tmem_base;
@@ -532,12 +535,18 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         {
             double* dstp = L ? L + (size_t)(gact ? b : b0) * nn + (size_t)pos * n : nullptr;
+            const unsigned rowb = wb + 8u * (unsigned)tri(pos);   // row pos of the position-ordered triangle
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 if (8 * c >= n)
                     break;
                 double v[8];
                 wip_tmem_load8(tw + 16u * c, v);
+                if constexpr (kSolve) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        sts_f64_if(has && 8 * c + u <= pos, rowb + 8u * (unsigned)(8 * c + u), v[u]);
+                }
                 if (dstp && has) {
                     if (wide) {
                         stg_v4f64(dstp + 8 * c, v[0], v[1], v[2], v[3]);
@@ -559,6 +568,18 @@ wipp_kernel(int n_rt, long long batch, const double* __restrict__ A, double* __r
         }
         if (K && gact && sub == 0)
             K[b] = kstart;
+        if constexpr (kSolve) {
+            // lane -> position through the (now free) panel area, then the substitutions on the
+            // position-ordered triangle
+            sts_f64(pnb + 8u * (unsigned)pos, (double)sub);
+            __syncwarp();
+            const unsigned tibs[1] = {tib};
+            const int rows[1] = {sub};
+            const bool rvs[1] = {has};
+            const int perms[1] = {(int)lds_f64(pnb + 8u * (unsigned)sub)};
+            const size_t off = (size_t)(gact ? b : b0) * nrhs * n;
+            wsm_solve_in_place<G, 1>(kFull, n, wb, tibs, rows, rvs, perms, Bm + off, X + off, nrhs);
+        }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -54,7 +54,7 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
     return cudaGetLastError();
 }
 
-// FAST mode, 16 < n <= 32, no fused solve: the implicit-pivoting kernels (wip_kernels.cuh).
+// FAST mode, 16 < n <= 32: the implicit-pivoting kernels (wip_kernels.cuh), kSolve: with the fused solve.
 // The launch attributes and the occupancy are queried once per instantiation and device.
 #ifndef MODCHOL_WIP_REGC
 #define MODCHOL_WIP_REGC 0   /* C fragments in registers (1) or in the shared-memory triangle (0) */
@@ -62,11 +62,12 @@ static cudaError_t launch_wsm(int n, long long batch, const double* a, double* l
 #ifndef MODCHOL_WIP_MINB
 #define MODCHOL_WIP_MINB (MODCHOL_WIP_REGC ? 5 : 8)
 #endif
-template <int kAlgo, int NB, int kN>
+template <int kAlgo, int NB, int kN, bool kSolve = false>
 static cudaError_t launch_wip(int n, long long batch, const double* a, double* l, double* e,
-                              unsigned long long* p, int* k, int sms, cudaStream_t st)
+                              unsigned long long* p, int* k, int sms, cudaStream_t st,
+                              const double* rhs = nullptr, double* x = nullptr, int nrhs = 0)
 {
-    auto kern = wip_kernel<kAlgo, NB, kN, MODCHOL_WIP_REGC != 0, MODCHOL_WIP_MINB>;
+    auto kern = wip_kernel<kAlgo, NB, kN, MODCHOL_WIP_REGC != 0, MODCHOL_WIP_MINB, kSolve>;
     constexpr size_t smem = (size_t)kWipWarps * kWipDoubles * sizeof(double);
     // The occupancy query answers 1 for any kernel that allocates tensor memory (it assumes all
     // 512 columns); this kernel takes kWipTmemCols per block, so the real limit is the register
@@ -93,17 +94,18 @@ static cudaError_t launch_wip(int n, long long batch, const double* a, double* l
     long long blocks = (batch + kWipWarps - 1) / kWipWarps;
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
-    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k, rhs, x, nrhs);
     return cudaGetLastError();
 }
 
-// FAST mode, 32 < n <= 64, no fused solve: the two-rows-per-lane implicit-pivoting kernels
+// FAST mode, 32 < n <= 64: the two-rows-per-lane implicit-pivoting kernels
 // (wip2_kernels.cuh); 256 tensor-memory columns and 84 KB of shared memory per block.
-template <int kAlgo, int NB, int kN>
+template <int kAlgo, int NB, int kN, bool kSolve = false>
 static cudaError_t launch_wip2(int n, long long batch, const double* a, double* l, double* e,
-                               unsigned long long* p, int* k, int sms, cudaStream_t st)
+                               unsigned long long* p, int* k, int sms, cudaStream_t st,
+                               const double* rhs = nullptr, double* x = nullptr, int nrhs = 0)
 {
-    auto kern = wip2_kernel<kAlgo, NB, kN, 2>;
+    auto kern = wip2_kernel<kAlgo, NB, kN, 2, kSolve>;
     constexpr size_t smem = (size_t)kWipWarps * kWip2Doubles * sizeof(double);
     static int occ_dev[64];
     int dev = 0;
@@ -127,16 +129,17 @@ static cudaError_t launch_wip2(int n, long long batch, const double* a, double* 
     long long blocks = (batch + kWipWarps - 1) / kWipWarps;
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
-    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k, rhs, x, nrhs);
     return cudaGetLastError();
 }
 
-// FAST mode, 4 < n <= 16, no fused solve: several matrices per warp (wipp_kernels.cuh)
-template <int kAlgo, int G, int kN>
+// FAST mode, 4 < n <= 16: several matrices per warp (wipp_kernels.cuh)
+template <int kAlgo, int G, int kN, bool kSolve = false>
 static cudaError_t launch_wipp(int n, long long batch, const double* a, double* l, double* e,
-                               unsigned long long* p, int* k, int sms, cudaStream_t st)
+                               unsigned long long* p, int* k, int sms, cudaStream_t st,
+                               const double* rhs = nullptr, double* x = nullptr, int nrhs = 0)
 {
-    auto kern = wipp_kernel<kAlgo, G, kN, 8>;
+    auto kern = wipp_kernel<kAlgo, G, kN, 8, kSolve>;
     constexpr int kGroups = 32 / G;
     constexpr size_t smem = (size_t)kWipWarps * kGroups * wpp_mat_doubles(G) * sizeof(double);
     static int occ_dev[64];
@@ -161,7 +164,7 @@ static cudaError_t launch_wipp(int n, long long batch, const double* a, double* 
     long long blocks = (batch + kWipWarps * kGroups - 1) / (kWipWarps * kGroups);
     const long long resident = (long long)sms * occ;
     if (blocks > resident) blocks = resident;   // persistent: every warp strides over the batch
-    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k);
+    kern<<<(unsigned)blocks, kWipWarps * 32, smem, st>>>(n, batch, a, l, e, p, k, rhs, x, nrhs);
     return cudaGetLastError();
 }
 
@@ -201,29 +204,33 @@ cudaError_t MODCHOL_CAT(launch_wsm_a, MODCHOL_INST_ALGO, _s, MODCHOL_INST_STRICT
 {
     constexpr int A = MODCHOL_INST_ALGO;
     constexpr bool S = MODCHOL_INST_STRICT != 0;
-    if (!S && x == nullptr && n > 8 && n <= 16 && wipp_enabled())
-        return n < 16 ? launch_wipp<A, 16, 0>(n, batch, a, l, e, p, k, sms, st)
-                      : launch_wipp<A, 16, 16>(n, batch, a, l, e, p, k, sms, st);
-    if (!S && x == nullptr && n > 4 && n <= 8 && wipp_enabled())
-        return n < 8 ? launch_wipp<A, 8, 0>(n, batch, a, l, e, p, k, sms, st)
-                     : launch_wipp<A, 8, 8>(n, batch, a, l, e, p, k, sms, st);
+    // FAST, 4 < n <= 64: the implicit-pivoting kernels, with the fused solve when x is given
+    if constexpr (!S) {
+        const bool sv = x != nullptr;
+#define MODCHOL_WIPX(fn, ...)                                                                      \
+    (sv ? fn<A, __VA_ARGS__, true>(n, batch, a, l, e, p, k, sms, st, rhs, x, nrhs)                 \
+        : fn<A, __VA_ARGS__, false>(n, batch, a, l, e, p, k, sms, st))
+        if (n > 8 && n <= 16 && wipp_enabled())
+            return n < 16 ? MODCHOL_WIPX(launch_wipp, 16, 0) : MODCHOL_WIPX(launch_wipp, 16, 16);
+        if (n > 4 && n <= 8 && wipp_enabled())
+            return n < 8 ? MODCHOL_WIPX(launch_wipp, 8, 0) : MODCHOL_WIPX(launch_wipp, 8, 8);
+        if (n > 16 && n <= 32 && wip_enabled() && (!sv || MODCHOL_WIP_REGC == 0))
+            return n <= 24 ? MODCHOL_WIPX(launch_wip, 3, 0)
+                   : n < 32 ? MODCHOL_WIPX(launch_wip, 4, 0) : MODCHOL_WIPX(launch_wip, 4, 32);
+        if (n > 32 && n <= 64 && wip2_enabled())
+            return n <= 48 ? MODCHOL_WIPX(launch_wip2, 6, 0)
+                   : n < 64 ? MODCHOL_WIPX(launch_wip2, 8, 0) : MODCHOL_WIPX(launch_wip2, 8, 64);
+#undef MODCHOL_WIPX
+    }
     if (n <= 4)
         return launch_wsm<A, 4, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 8)
         return launch_wsm<A, 8, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
     if (n <= 16)
         return launch_wsm<A, 16, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
-    if (!S && x == nullptr && n > 16 && n <= 32 && wip_enabled())
-        return n <= 24 ? launch_wip<A, 3, 0>(n, batch, a, l, e, p, k, sms, st)
-               : n < 32 ? launch_wip<A, 4, 0>(n, batch, a, l, e, p, k, sms, st)
-                        : launch_wip<A, 4, 32>(n, batch, a, l, e, p, k, sms, st);
     if (n <= 32)
         return wsm_pack_pref() ? launch_wsm<A, 16, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st)
                                : launch_wsm<A, 32, 1, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
-    if (!S && x == nullptr && n > 32 && n <= 64 && wip2_enabled())
-        return n <= 48 ? launch_wip2<A, 6, 0>(n, batch, a, l, e, p, k, sms, st)
-               : n < 64 ? launch_wip2<A, 8, 0>(n, batch, a, l, e, p, k, sms, st)
-                        : launch_wip2<A, 8, 64>(n, batch, a, l, e, p, k, sms, st);
     return launch_wsm<A, 32, 2, S>(n, batch, a, l, e, p, k, rhs, x, nrhs, sms, st);
 }
 
