@@ -118,7 +118,7 @@ int modchol_solve_batched_f64(int64_t batch, int32_t n, int32_t nrhs, const doub
 
 /* The same consumer step FUSED with the factorisation: factorise a_b with `algo` and solve
  * (A_b + E_b) x = b for nrhs right-hand sides per matrix in one call.  For n <= 64 this is ONE
- * kernel and the factor never leaves shared memory, so L does not round-trip through HBM
+ * kernel and the factor never leaves the SM (shared / tensor memory), so L does not round-trip through HBM
  * (n = 32: 6.4 KB read + 0.25 KB written per matrix instead of 16.9 KB + the solve's 8.5 KB);
  * larger n run the factor kernel into scratch followed by the solve kernel.
  *   b, x : batch x nrhs x n f64; x may alias b.
