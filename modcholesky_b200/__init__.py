@@ -32,7 +32,7 @@ def launch_count() -> int:
 
 
 def set_small_kernel_family(family) -> int:
-    """0/'auto', 1/'reg' (register-resident), 2/'wsm' (shared-memory-resident): which kernel family
-    serves n <= 32 for SE90/SE99.  Returns the previous setting."""
-    ids = {"auto": 0, "reg": 1, "wsm": 2}
+    """0/'auto', 1/'reg' (register-resident), 2/'wsm' (shared-memory-resident), 3/'tpm' (one thread
+    per matrix, n <= 8): which kernel family serves n <= 32.  Returns the previous setting."""
+    ids = {"auto": 0, "reg": 1, "wsm": 2, "tpm": 3}
     return int(lib().modchol_set_small_kernel_family(ids.get(family, family)))

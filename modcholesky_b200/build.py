@@ -20,7 +20,7 @@ NVCC_FLAGS = [
 ]
 
 # (source, object name, extra defines)
-UNITS = [("modchol_api.cu", "api.o", []), ("bsm_inst.cu", "bsm.o", [])] + [
+UNITS = [("modchol_api.cu", "api.o", []), ("bsm_inst.cu", "bsm.o", []), ("tpm_inst.cu", "tpm.o", [])] + [
     ("lwm_inst.cu", f"lwm_a{a}.o", [f"-DMODCHOL_INST_ALGO={a}"]) for a in (0, 1, 2)
 ] + [
     ("warp_inst.cu", f"warp_a{a}_s{s}.o", [f"-DMODCHOL_INST_ALGO={a}", f"-DMODCHOL_INST_STRICT={s}"])

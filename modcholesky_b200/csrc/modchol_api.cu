@@ -220,23 +220,32 @@ int slot_reserve(Slot& s, size_t mats, int n)
 }
 
 // ---- size-class dispatch ---------------------------------------------------------------
-enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3, kClsCtaPacked = 4, kClsCtaBlocked = 5, kClsWarpPanel = 6 };
+enum KernelClass { kClsWarp = 0, kClsCtaSmem = 1, kClsCtaGmem = 2, kClsWarpSmem = 3, kClsCtaPacked = 4, kClsCtaBlocked = 5, kClsWarpPanel = 6, kClsThread = 7 };
 
-// Which small-n family serves n <= 32 (0 auto, 1 registers, 2 shared memory); initialised
-// from MODCHOL_SMALL_KERNEL=reg|wsm, changed by modchol_set_small_kernel_family().
+// Which small-n family serves n <= 32 (0 auto, 1 registers, 2 shared memory, 3 thread per matrix
+// wherever it exists); initialised from MODCHOL_SMALL_KERNEL=reg|wsm|tpm, changed by
+// modchol_set_small_kernel_family().
 std::atomic<int> g_small_family{-1};
 int small_kernel_pref()
 {
     int v = g_small_family.load();
     if (v < 0) {
         const char* e = getenv("MODCHOL_SMALL_KERNEL");
-        v = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'w' ? 2 : 0));
+        v = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'w' ? 2 : (e[0] == 't' ? 3 : 0)));
         g_small_family.store(v);
     }
     return v;
 }
 
 int cta_ld(int n) { return (n & 1) ? n : n + 1; }
+
+// largest n served by the thread-per-matrix kernels by default (MODCHOL_TPM_MAX, tuning knob read
+// per call; 0 switches them off)
+int tpm_max_n()
+{
+    const char* e = getenv("MODCHOL_TPM_MAX");
+    return e ? atoi(e) : 4;
+}
 
 // smallest n served by the blocked large-n kernels (MODCHOL_BSM_MIN, tuning knob)
 int bsm_min_n()
@@ -267,6 +276,8 @@ KernelClass classify(int algo, int mode, int n, int smem_optin)
     // modes for all but a few (n <= 8, STRICT, mixed-phase) cases, and it is the only warp-level
     // kernel for 32 < n <= 64 -- it is the default; the register family stays selectable.
     const bool auto_wsm = wsm_ok;
+    if (tpm_kernel_available(algo, n) && (pref == 3 || (pref == 0 && n <= tpm_max_n())))
+        return kClsThread;
     if (wsm_ok && (pref == 2 || (pref == 0 && auto_wsm) || !reg_ok))
         return kClsWarpSmem;
     if (reg_ok)
@@ -325,6 +336,13 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
         g_launches.fetch_add(1);
         if (ce != cudaSuccess)
             return fail(MODCHOL_ERR_CUDA, "warp kernel launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    if (cls == kClsThread) {
+        cudaError_t ce = launch_tpm_kernel(algo, n, batch, a, l, e, p, k, c.sms, st);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "tpm kernel launch failed: %s", cudaGetErrorString(ce));
         return MODCHOL_OK;
     }
     if (cls == kClsWarpSmem) {
@@ -517,7 +535,9 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
         return rc;
     const DeviceCtx& c = g_ctx[dev];
     // every shared-memory warp class (n <= 64, both modes) carries its own fused solve
-    const bool fused = classify(algo, mode, n, c.smem_optin) == kClsWarpSmem;
+    // (the thread-per-matrix class has no solve of its own: its sizes keep the fused warp kernels)
+    const KernelClass cls = classify(algo, mode, n, c.smem_optin);
+    const bool fused = cls == kClsWarpSmem || cls == kClsThread;
     if (fused) {
         cudaError_t ce = launch_wsm_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st, b, x, nrhs);
         g_launches.fetch_add(1);
@@ -671,7 +691,7 @@ int64_t modchol_launch_count(void) { return g_launches.load(); }
 int modchol_set_small_kernel_family(int family)
 {
     const int prev = small_kernel_pref();
-    g_small_family.store(family == 1 || family == 2 ? family : 0);
+    g_small_family.store(family >= 1 && family <= 3 ? family : 0);
     return prev;
 }
 
@@ -681,6 +701,7 @@ const char* modchol_kernel_class(int algo, int mode, int32_t n)
         return "unsupported";
     switch (classify(algo, mode, n, 0)) {
     case kClsWarp: return "warp32";
+    case kClsThread: return "thread";
     case kClsWarpSmem: return "warp_smem";
     case kClsCtaPacked: return "cta_packed";
     case kClsCtaBlocked: return "cta_blocked";

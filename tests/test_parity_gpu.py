@@ -159,16 +159,19 @@ def test_strict_bit_exact_vs_oracle(oracle, torch_cuda, algo, n):
         _assert_bit_exact(f"{algo} n={n} {fam}", _gpu(torch_cuda, algo, a, "strict"), ref)
 
 
-@pytest.mark.parametrize("family", ["reg", "wsm"])
+@pytest.mark.parametrize("family", ["reg", "wsm", "tpm"])
 def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
-    """n <= 32 has two kernel families (shared-memory-resident by default, register-resident on
-    request); both must give the oracle's bits."""
+    """n <= 32 has two warp-level kernel families (shared-memory-resident by default,
+    register-resident on request) and n <= 8 a thread-per-matrix one (the default for n <= 4); all
+    must give the oracle's bits."""
     prev = m.set_small_kernel_family(family)
     try:
         for algo in ALGOS:
             for n in (1, 2, 3, 4, 5, 8, 9, 16, 17, 31, 32):
+                if family == "tpm" and n > 8:
+                    continue
                 for mode in ("strict", "fast"):
-                    assert m.kernel_class(algo, n, mode) == ("warp32" if family == "reg" else "warp_smem")
+                    assert m.kernel_class(algo, n, mode) == {"reg": "warp32", "wsm": "warp_smem", "tpm": "thread"}[family]
                 for fam in ("uniform", "wishart", "ties"):
                     a = matgen.make(fam, 4000 + n, 64, n)
                     ref = oracle.factor_batched(algo, a)
@@ -178,6 +181,30 @@ def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
                                           _gpu(torch_cuda, algo, a, "fast"), ref)
     finally:
         m.set_small_kernel_family(prev)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
+    """One thread per matrix (tpm_kernels.cuh): tiles of 128 matrices -- batches below one tile,
+    of several tiles and with a ragged last tile; both modes run the reference's arithmetic, so
+    FAST is bit-exact too; every family including exact ties and the bench-style Q D Q^T inputs."""
+    torch = torch_cuda
+    prev = m.set_small_kernel_family("tpm")
+    try:
+        for algo in ALGOS:
+            for b, fam in ((1, "uniform"), (37, "wishart"), (128, "pd"), (129, "ties"), (1000, "uniform"),
+                           (515, "bench"), (300, "wishart")):
+                if fam == "bench" and n < 3:
+                    continue
+                a = matgen.make(fam, 8800 + 10 * n + b, b, n)
+                ref = oracle.factor_batched(algo, a)
+                for mode in ("strict", "fast"):
+                    assert m.kernel_class(algo, n, mode) == "thread"
+                    _assert_bit_exact(f"tpm {algo} n={n} {fam} b={b} {mode}", _gpu(torch, algo, a, mode), ref)
+    finally:
+        m.set_small_kernel_family(prev)
+    # the default dispatch serves n <= 4 with these kernels
+    assert m.kernel_class("se99", 4, "fast") == "thread" and m.kernel_class("se99", 9, "fast") == "warp_smem"
 
 
 def test_packed_shared_memory_variant_is_bit_exact(oracle, torch_cuda, monkeypatch):
