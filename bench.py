@@ -141,6 +141,8 @@ def kernel_name(m, algo, n, mode):
         if n <= 32:
             return f"{cls}: wip_kernel<{A}, n={n}> (implicit pivoting, L in tensor memory, DMMA rank-8 updates)"
         return f"{cls}: wip2_kernel<{A}> (implicit pivoting, two rows per lane, L in tensor memory, DMMA updates)"
+    if cls == "thread":
+        return f"{cls}: tpr_kernel<{A}, N={n}> (one thread per matrix, lower triangle in registers, tile staged through shared memory)"
     if cls == "cta_blocked":
         return f"{cls}: {'bsm_gmw_kernel' if algo == 'gmw81' else 'bsm_se_kernel'}<{A}> (panel in shared memory, DMMA trailing update from L2)"
     names = {"warp_smem": "wsm_gmw_kernel" if algo == "gmw81" else "wsm_se_kernel",
@@ -222,6 +224,31 @@ def other_configs(torch, np, m, dev, peak):
         out[key] = ent
         del a, d, resid, flags
         torch.cuda.empty_cache()
+
+    # the reference's fixed-size bench shapes 3x3 / 4x4 (benches/bench.rs:23-44 and the se90 / se99
+    # twins), batched: 2^22 symmetric-uniform matrices through the thread-per-matrix kernels
+    small = {}
+    for n in (3, 4):
+        batch = 1 << 22
+        a = gen_batch(torch, batch, n, SEED + 17 * n, dev)
+        ent = {}
+        for algo in ("gmw81", "se90", "se99"):
+            c = device_case(algo, n, batch, a, f"{algo} n={n}")
+            ent[algo] = {"fast": {k: c["fast"][k] for k in ("matrices_per_sec", "ms_per_step", "kernel")},
+                         "fast_roofline_frac": c["fast"]["roofline"]["frac"],
+                         "strict_matrices_per_sec": c["strict"]["matrices_per_sec"],
+                         "strict_roofline_frac": c["strict"]["roofline"]["frac"]}
+        ah = a[:4096].cpu().numpy()
+        ds = m.factor_batched("se99", a[:4096], mode="fast")
+        ref = oracle.factor_batched("se99", ah, threads=0)
+        ent["fast_bit_exact_vs_oracle"] = bool(np.array_equal(ds.l.cpu().numpy(), ref.l)
+                                               and np.array_equal(ds.e.cpu().numpy(), ref.e)
+                                               and np.array_equal(ds.p.cpu().numpy().astype(np.uint64), ref.p))
+        ent["batch"] = batch
+        small[f"n={n}"] = ent
+        del a
+        torch.cuda.empty_cache()
+    out["small_n_thread_per_matrix"] = small
 
     # the reference's bench family on its own shapes (benches/bench.rs:46-83): Q D Q^T with the
     # bit-exact seeded factors, assembled on the device; the CPU column is the oracle on the

@@ -371,4 +371,434 @@ tpm_kernel(int n, long long batch, const double* __restrict__ A, double* __restr
     }
 }
 
+
+// ================================================================================================
+// The same thread-per-matrix scheme with COMPILE-TIME n (tpr_kernel<kAlgo, N>, N <= kTprMaxN):
+// every loop unrolled, the lower triangle, g / d, e and p in REGISTERS.  The run-time-n kernel
+// above spends four of five instructions on index arithmetic, loop control and shared-memory
+// traffic (profiles/r02_tpm_se99_n4_summary.txt: 106 warp-instructions per 4x4 matrix, 12 of them
+// FP64); here the only run-time index is the pivot row m, and the exchange j <-> m becomes a chain
+// of predicated register swaps over the candidates r = j+1 .. N-1.
+// Storage is the LOWER triangle only: the reference keeps both triangles of its working matrix
+// bit-identical (mirror stores se90.rs:91, se99.rs:103,169; the two divisions by l_jj act on equal
+// values), so for the symmetric inputs the crate is specified for, every value it reads from the
+// upper triangle is the lower one's -- the arithmetic below is still the reference's, element for
+// element, and the results are bit-identical (tests/test_parity_gpu.py).
+// ================================================================================================
+constexpr int kTprMaxN = 8;
+
+__device__ __forceinline__ void tpr_cswap(bool c, double& a, double& b)
+{
+    const double t = a;
+    a = c ? b : a;
+    b = c ? t : b;
+}
+__device__ __forceinline__ void tpr_cswap(bool c, int& a, int& b)
+{
+    const int t = a;
+    a = c ? b : a;
+    b = c ? t : b;
+}
+
+template <int N>
+struct TprTri {
+    double v[N * (N + 1) / 2];
+    __device__ __forceinline__ double& operator()(int i, int k) { return v[i * (i + 1) / 2 + k]; }   // i >= k
+};
+
+// symmetric exchange of rows / columns J and m (J < m): utils.rs:41-49 + :30-38 on lower storage,
+// as predicated swaps over the candidates r
+template <int N, int J>
+__device__ __forceinline__ void tpr_sym_cswap(TprTri<N>& a, int m)
+{
+#pragma unroll
+    for (int r = J + 1; r < N; ++r) {
+        const bool c = m == r;
+        tpr_cswap(c, a(J, J), a(r, r));
+#pragma unroll
+        for (int k = 0; k < J; ++k)
+            tpr_cswap(c, a(J, k), a(r, k));
+#pragma unroll
+        for (int k = J + 1; k < r; ++k)
+            tpr_cswap(c, a(k, J), a(r, k));
+#pragma unroll
+        for (int k = r + 1; k < N; ++k)
+            tpr_cswap(c, a(k, J), a(k, r));
+    }
+}
+template <int N, int J, typename T>
+__device__ __forceinline__ void tpr_vec_cswap(T (&v)[N], int m)
+{
+#pragma unroll
+    for (int r = J + 1; r < N; ++r)
+        tpr_cswap(m == r, v[J], v[r]);
+}
+
+// se90.rs:84-93 == :142-151 == se99.rs:96-105 == :162-171 on the lower triangle
+template <int N, int J>
+__device__ __forceinline__ void tpr_eliminate(TprTri<N>& l)
+{
+    const double ljj = dsqrt(l(J, J));
+    l(J, J) = ljj;
+#pragma unroll
+    for (int i = J + 1; i < N; ++i) {
+        const double lij = ddiv(l(i, J), ljj);
+        l(i, J) = lij;
+#pragma unroll
+        for (int k = J + 1; k <= i; ++k)
+            l(i, k) = dsub(l(i, k), dmul(lij, l(k, J)));
+    }
+}
+
+template <int N>
+struct TprSe {
+    TprTri<N> l;
+    double g[N], e[N];
+    int p[N];
+    double gamma, taugamma, delta_prev;
+    bool ph1;
+    int kstart;
+};
+
+// column J of SE90 / SE99: the phase-1 step (or the switch to phase 2), then the phase-2 step
+template <int kAlgo, int N, int J>
+__device__ __forceinline__ void tpr_se_step(TprSe<N>& s)
+{
+    TprTri<N>& l = s.l;
+    if (s.ph1) {   // phase 1: se90.rs:61-96, se99.rs:61-109
+        if (kAlgo == kSE99) {   // se99.rs:62-73
+            double dmax = -INFINITY, dmin = INFINITY;
+#pragma unroll
+            for (int i = J; i < N; ++i) {
+                const double x = l(i, i);
+                if (x > dmax) dmax = x;
+                if (x < dmin) dmin = x;
+            }
+            if (dmax < s.taugamma || dmin < dmul(-MODCHOL_MU, dmax))
+                s.ph1 = false;
+        }
+        if (s.ph1) {
+            int m = J;   // utils.rs:52-70: first strict maximum, a NaN head sticks
+            double best = l(J, J);
+#pragma unroll
+            for (int i = J + 1; i < N; ++i) {
+                const double c = l(i, i);
+                if (c > best) {
+                    best = c;
+                    m = i;
+                }
+            }
+            tpr_sym_cswap<N, J>(l, m);   // se90.rs:63-68, se99.rs:76-81
+            tpr_vec_cswap<N, J>(s.p, m);
+            double la = INFINITY;   // se90.rs:70-77, se99.rs:82-89
+            const double ljj = l(J, J);
+#pragma unroll
+            for (int i = J + 1; i < N; ++i) {
+                const double lij = l(i, J);
+                const double nv = dsub(l(i, i), ddiv(dmul(lij, lij), ljj));
+                if (nv < la)
+                    la = nv;
+            }
+            const double thresh = kAlgo == kSE99 ? dmul(-MODCHOL_MU, s.gamma) : s.taugamma;   // se99.rs:90 / se90.rs:78
+            if (la < thresh)
+                s.ph1 = false;
+        }
+        if (s.ph1) {
+            tpr_eliminate<N, J>(l);
+        } else {
+            s.kstart = J;   // phase 2 starts at this column
+            if (kAlgo == kSE99 && J == N - 1) {   // se99.rs:115-119
+                const double ljj = l(J, J);
+                const double ej = tail1x1_e(ljj, s.gamma);
+                s.e[J] = ej;
+                l(J, J) = dsqrt(dadd(ljj, ej));
+            } else if (kAlgo == kSE90 || J + 1 < N) {
+                // lower Gershgorin bounds of the trailing block, se90.rs:105-110, se99.rs:125-130
+#pragma unroll
+                for (int i = J; i < N; ++i) {
+                    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                    for (int q = J; q < i; ++q)
+                        s1 = dadd(s1, fabs(l(i, q)));
+#pragma unroll
+                    for (int r = i + 1; r < N; ++r)
+                        s2 = dadd(s2, fabs(l(r, i)));
+                    s.g[i] = dsub(dsub(l(i, i), s1), s2);
+                }
+            }
+        }
+    }
+    if constexpr (J + 2 < N) {
+        if (!s.ph1) {   // phase-2 step, se90.rs:113-152, se99.rs:133-172
+            int m = J;
+            double best = s.g[J];
+#pragma unroll
+            for (int i = J + 1; i < N; ++i) {
+                const double c = s.g[i];
+                if (c > best) {
+                    best = c;
+                    m = i;
+                }
+            }
+            tpr_sym_cswap<N, J>(l, m);
+            tpr_vec_cswap<N, J>(s.p, m);
+            tpr_vec_cswap<N, J>(s.g, m);
+            double normj = 0.0;   // se90.rs:124-131, se99.rs:144-151
+#pragma unroll
+            for (int r = J + 1; r < N; ++r)
+                normj = dadd(normj, fabs(l(r, J)));
+            double ljj = l(J, J);
+            const double ej = phase2_e(ljj, normj, s.taugamma, s.delta_prev);
+            s.e[J] = ej;
+            if (ej > 0.0) {
+                ljj = dadd(ljj, ej);
+                l(J, J) = ljj;
+                s.delta_prev = ej;
+            }
+            if (fabs(dsub(ljj, normj)) > MODCHOL_EPS) {   // se90.rs:134-139, se99.rs:154-159
+                const double t = dsub(1.0, ddiv(normj, ljj));
+#pragma unroll
+                for (int i = J + 1; i < N; ++i)
+                    s.g[i] = dadd(s.g[i], dmul(fabs(l(i, J)), t));
+            }
+            tpr_eliminate<N, J>(l);
+        }
+    }
+}
+template <int kAlgo, int N, int J>
+__device__ __forceinline__ void tpr_se_steps(TprSe<N>& s)
+{
+    if constexpr (J < N) {
+        tpr_se_step<kAlgo, N, J>(s);
+        tpr_se_steps<kAlgo, N, J + 1>(s);
+    }
+}
+
+// SE90 / SE99 on the lower triangle in s.l; leaves L there, e by position, p; returns kstart
+template <int kAlgo, int N>
+__device__ __forceinline__ void tpr_se(TprSe<N>& s)
+{
+    TprTri<N>& l = s.l;
+    s.gamma = 0.0;   // se90.rs:55-57, se99.rs:54-56
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        s.e[i] = 0.0;
+        s.p[i] = i;
+        s.g[i] = 0.0;
+        const double d = fabs(l(i, i));
+        if (d > s.gamma)
+            s.gamma = d;
+    }
+    s.taugamma = dmul(MODCHOL_TAU, s.gamma);
+    s.ph1 = true;
+    s.kstart = -1;
+    s.delta_prev = 0.0;
+    tpr_se_steps<kAlgo, N, 0>(s);
+    if constexpr (N >= 2) {
+        if (!s.ph1 && (kAlgo == kSE90 || s.kstart + 1 < N)) {   // final 2x2: se90.rs:155-166, se99.rs:175-186
+            double lhi, llo;
+            const double off = l(N - 1, N - 2);   // m[0,1] == m[1,0] (symmetric working matrix)
+            eigenvalues_2x2(l(N - 2, N - 2), off, off, l(N - 1, N - 1), lhi, llo);
+            const double en = tail2x2_e(kAlgo, lhi, llo, s.gamma, s.delta_prev);
+            s.e[N - 2] = en;
+            s.e[N - 1] = en;
+            if (en > 0.0) {
+                l(N - 2, N - 2) = dadd(l(N - 2, N - 2), en);
+                l(N - 1, N - 1) = dadd(l(N - 1, N - 1), en);
+            }
+            const double l00 = dsqrt(l(N - 2, N - 2));
+            l(N - 2, N - 2) = l00;
+            const double l10 = ddiv(off, l00);
+            l(N - 1, N - 2) = l10;
+            l(N - 1, N - 1) = dsqrt(dsub(l(N - 1, N - 1), dmul(l10, l10)));
+        }
+    }
+}
+
+template <int N>
+struct TprGmw {
+    TprTri<N> l, c;
+    double d[N], e[N];
+    int p[N];
+    double beta, delta;
+};
+
+// column J of GMW81 (gmw81.rs:70-111)
+template <int N, int J>
+__device__ __forceinline__ void tpr_gmw_step(TprGmw<N>& s)
+{
+    TprTri<N>&l = s.l, &c = s.c;
+    int m = J;   // utils.rs:73-91 on the diagonal of c (gmw81.rs:71-78)
+    double best = fabs(c(J, J));
+#pragma unroll
+    for (int i = J + 1; i < N; ++i) {
+        const double v = fabs(c(i, i));
+        if (v > best) {
+            best = v;
+            m = i;
+        }
+    }
+    tpr_sym_cswap<N, J>(c, m);
+    tpr_sym_cswap<N, J>(l, m);
+    tpr_vec_cswap<N, J>(s.p, m);
+#pragma unroll
+    for (int q = 0; q < J; ++q)   // gmw81.rs:79-81
+        l(J, q) = ddiv(c(J, q), s.d[q]);
+#pragma unroll
+    for (int i = J; i < N; ++i) {   // gmw81.rs:83-85
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < J; ++q)
+            acc = dadd(acc, dmul(l(J, q), c(i, q)));
+        c(i, J) = dsub(l(i, J), acc);
+    }
+    double theta = 0.0;   // gmw81.rs:87-100
+#pragma unroll
+    for (int i = J + 1; i < N; ++i) {
+        const double v = fabs(c(i, J));
+        if (v > theta)
+            theta = v;
+    }
+    const double tb = ddiv(theta, s.beta);
+    const double cjj = c(J, J);
+    const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), s.delta);   // gmw81.rs:102
+    s.d[J] = dj;
+#pragma unroll
+    for (int i = J + 1; i < N; ++i) {   // gmw81.rs:104-109
+        const double cij = c(i, J);
+        c(i, i) = dsub(c(i, i), ddiv(dmul(cij, cij), dj));
+    }
+    s.e[J] = dsub(dj, cjj);   // gmw81.rs:110
+}
+template <int N, int J>
+__device__ __forceinline__ void tpr_gmw_steps(TprGmw<N>& s)
+{
+    if constexpr (J < N) {
+        tpr_gmw_step<N, J>(s);
+        tpr_gmw_steps<N, J + 1>(s);
+    }
+}
+
+// GMW81 on the lower triangle in s.l (gmw81.rs:39-134); leaves L there
+template <int N>
+__device__ __forceinline__ void tpr_gmw(TprGmw<N>& s)
+{
+    TprTri<N>&l = s.l, &c = s.c;
+    double diag_max = 0.0, off_max = 0.0;   // gmw81.rs:49-58 (the upper triangle mirrors the lower)
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        s.e[i] = 0.0;
+        s.d[i] = 0.0;
+        s.p[i] = i;
+#pragma unroll
+        for (int q = 0; q <= i; ++q) {
+            const double v = fabs(l(i, q));
+            if (i == q) {
+                if (v > diag_max) diag_max = v;
+            } else if (v > off_max) {
+                off_max = v;
+            }
+            c(i, q) = i == q ? l(i, q) : 0.0;   // gmw81.rs:66-68
+        }
+    }
+    const double nf = (double)N;
+    s.delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(diag_max, off_max)));   // gmw81.rs:60
+    s.beta = dsqrt(fmax(fmax(diag_max, ddiv(off_max, dsqrt(dsub(dmul(nf, nf), 1.0)))), MODCHOL_EPS));   // :61-64
+    tpr_gmw_steps<N, 0>(s);
+    // gmw81.rs:112-125: l . diag(sqrt(d)) with a unit diagonal; the dense product's accumulation
+    // from 0.0 turns a -0 into +0
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int q = 0; q <= i; ++q)
+            l(i, q) = dadd(0.0, q == i ? dsqrt(s.d[q]) : dmul(l(i, q), dsqrt(s.d[q])));
+}
+
+// doubles of shared memory per thread: the matrix (stride N N | 1), then e and p (stride N | 1)
+__host__ __device__ constexpr int tpr_thread_doubles(int n) { return tpm_mat_stride(n) + 2 * tpm_vec_stride(n); }
+
+template <int kAlgo, int N>
+__global__ void __launch_bounds__(kTpmThreads)
+tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L,
+           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    extern __shared__ double sm[];
+    constexpr int NN = N * N, S = tpm_mat_stride(N), V = tpm_vec_stride(N);
+    const int tid = threadIdx.x;
+    double* mats = sm;                       // kTpmThreads x S
+    double* evec = mats + kTpmThreads * S;   // e, original order
+    unsigned long long* pvec = reinterpret_cast<unsigned long long*>(evec + kTpmThreads * V);
+
+    for (long long t0 = (long long)blockIdx.x * kTpmThreads; t0 < batch; t0 += (long long)gridDim.x * kTpmThreads) {
+        const int cnt = (int)min((long long)kTpmThreads, batch - t0);
+        const int words = cnt * NN;
+        {   // ---- in: coalesced over the tile, matrix by matrix into shared memory ---------------
+            const double* src = A + (size_t)t0 * NN;
+            for (int q = tid; q < words; q += kTpmThreads)
+                mats[q + (S - NN) * (q / NN)] = __ldg(src + q);
+        }
+        __syncthreads();
+        int kstart = -1;
+        if (tid < cnt) {
+            double* mine = mats + tid * S;
+            double* eo = evec + tid * V;
+            unsigned long long* po = pvec + tid * V;
+            if constexpr (kAlgo == kGMW81) {
+                TprGmw<N> s;
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+#pragma unroll
+                    for (int q = 0; q <= i; ++q)
+                        s.l(i, q) = mine[i * N + q];
+                tpr_gmw<N>(s);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+#pragma unroll
+                    for (int q = 0; q < N; ++q)
+                        mine[i * N + q] = q <= i ? s.l(i, q) : 0.0;   // gmw81.rs:119-123
+                    eo[s.p[i]] = s.e[i];                                // gmw81.rs:127-131
+                    po[i] = (unsigned long long)s.p[i];
+                }
+            } else {
+                TprSe<N> s;
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+#pragma unroll
+                    for (int q = 0; q <= i; ++q)
+                        s.l(i, q) = mine[i * N + q];
+                tpr_se<kAlgo, N>(s);
+                kstart = s.kstart;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+#pragma unroll
+                    for (int q = 0; q < N; ++q)
+                        mine[i * N + q] = q <= i ? s.l(i, q) : 0.0;   // se90.rs:169-173, se99.rs:189-192
+                    eo[s.p[i]] = s.e[i];                                // se90.rs:174-178, se99.rs:194-198
+                    po[i] = (unsigned long long)s.p[i];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- out -------------------------------------------------------------------------------
+        if (L) {
+            double* dst = L + (size_t)t0 * NN;
+            for (int q = tid; q < words; q += kTpmThreads)
+                dst[q] = mats[q + (S - NN) * (q / NN)];
+        }
+        {
+            const int vwords = cnt * N;
+            for (int q = tid; q < vwords; q += kTpmThreads) {
+                const int at = q + (V - N) * (q / N);
+                if (E)
+                    E[(size_t)t0 * N + q] = evec[at];
+                if (P)
+                    P[(size_t)t0 * N + q] = pvec[at];
+            }
+        }
+        if (K && tid < cnt)
+            K[t0 + tid] = kstart;
+        __syncthreads();   // the tile's shared memory is free again
+    }
+}
+
 }  // namespace modchol

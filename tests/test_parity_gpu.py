@@ -162,7 +162,7 @@ def test_strict_bit_exact_vs_oracle(oracle, torch_cuda, algo, n):
 @pytest.mark.parametrize("family", ["reg", "wsm", "tpm"])
 def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
     """n <= 32 has two warp-level kernel families (shared-memory-resident by default,
-    register-resident on request) and n <= 8 a thread-per-matrix one (the default for n <= 4); all
+    register-resident on request) and n <= 8 a thread-per-matrix one (the default there); all
     must give the oracle's bits."""
     prev = m.set_small_kernel_family(family)
     try:
@@ -203,8 +203,8 @@ def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
                     _assert_bit_exact(f"tpm {algo} n={n} {fam} b={b} {mode}", _gpu(torch, algo, a, mode), ref)
     finally:
         m.set_small_kernel_family(prev)
-    # the default dispatch serves n <= 4 with these kernels
-    assert m.kernel_class("se99", 4, "fast") == "thread" and m.kernel_class("se99", 9, "fast") == "warp_smem"
+    # the default dispatch serves n <= 8 with these kernels
+    assert m.kernel_class("se99", 8, "fast") == "thread" and m.kernel_class("se99", 9, "fast") == "warp_smem"
 
 
 def test_packed_shared_memory_variant_is_bit_exact(oracle, torch_cuda, monkeypatch):
