@@ -141,6 +141,8 @@ def kernel_name(m, algo, n, mode):
         if n <= 32:
             return f"{cls}: wip_kernel<{A}, n={n}> (implicit pivoting, L in tensor memory, DMMA rank-8 updates)"
         return f"{cls}: wip2_kernel<{A}> (implicit pivoting, two rows per lane, L in tensor memory, DMMA updates)"
+    if cls == "thread" and n > 8:
+        return f"{cls}: tps_kernel<{A}, N={n}> (one thread per matrix, lower triangle in thread-private shared memory)"
     if cls == "thread":
         return f"{cls}: tpr_kernel<{A}, N={n}> (one thread per matrix, lower triangle in registers, tile staged through shared memory)"
     if cls == "cta_blocked":

@@ -24,20 +24,45 @@ static cudaError_t launch_tpm_algo(int n, long long batch, const double* a, doub
     return cudaGetLastError();
 }
 
-// compile-time n, everything in registers (n <= kTprMaxN)
+// compile-time n, everything in registers (n <= kTprMaxN).  Direct per-thread global accesses
+// where one thread moves at least a sector's worth per instruction pair (n = 2, 8), the tile
+// staged through shared memory otherwise (measured: profiles/r02_thread_per_matrix.txt).
 template <int kAlgo, int N>
 static cudaError_t launch_tpr_n(long long batch, const double* a, double* l, double* e,
                                 unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
-    auto kern = tpr_kernel<kAlgo, N>;
-    constexpr size_t smem = (size_t)kTpmThreads * tpr_thread_doubles(N) * sizeof(double);
-    int occ = 1;
-    cudaError_t ce = cached_occupancy(kern, kTpmThreads, smem, smem, &occ);
-    if (ce != cudaSuccess) return ce;
+    constexpr bool kDirect = N == 2 || N == 8;
     long long blocks = (batch + kTpmThreads - 1) / kTpmThreads;
-    const long long resident = (long long)sms * occ;
-    if (blocks > resident) blocks = resident;
-    kern<<<(unsigned)blocks, kTpmThreads, smem, st>>>(batch, a, l, e, p, k);
+    if constexpr (kDirect) {
+        auto kern = tpr_kernel<kAlgo, N>;
+        // no shared memory: the whole carve-out goes to L1, which serves the rest of each sector a
+        // thread has touched (queried once per device)
+        static int occ_dev[64];
+        int dev = 0;
+        cudaError_t ce = cudaGetDevice(&dev);
+        if (ce != cudaSuccess) return ce;
+        int occ = dev < 64 ? occ_dev[dev] : 0;
+        if (occ == 0) {
+            ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1);
+            if (ce != cudaSuccess) return ce;
+            ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTpmThreads, 0);
+            if (ce != cudaSuccess) return ce;
+            if (occ < 1) occ = 1;
+            if (dev < 64) occ_dev[dev] = occ;   // benign race: every writer stores the same value
+        }
+        const long long resident = (long long)sms * occ;
+        if (blocks > resident) blocks = resident;
+        kern<<<(unsigned)blocks, kTpmThreads, 0, st>>>(batch, a, l, e, p, k);
+    } else {
+        auto kern = tpr_kernel_staged<kAlgo, N>;
+        constexpr size_t smem = (size_t)kTpmThreads * tpr_thread_doubles(N) * sizeof(double);
+        int occ = 1;
+        cudaError_t ce = cached_occupancy(kern, kTpmThreads, smem, smem, &occ);
+        if (ce != cudaSuccess) return ce;
+        const long long resident = (long long)sms * occ;
+        if (blocks > resident) blocks = resident;
+        kern<<<(unsigned)blocks, kTpmThreads, smem, st>>>(batch, a, l, e, p, k);
+    }
     return cudaGetLastError();
 }
 template <int kAlgo>
@@ -58,6 +83,46 @@ static cudaError_t launch_tpr_algo(int n, long long batch, const double* a, doub
 }
 static_assert(kTprMaxN == 8, "launch_tpr_algo lists the instantiations");
 
+// 8 < n <= kTpsMaxN, SE90 / SE99: compile-time n, the triangle in thread-private shared memory
+template <int kAlgo, int N>
+static cudaError_t launch_tps_n(long long batch, const double* a, double* l, double* e,
+                                unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    // staged (coalesced) tile copies up to n = 11, direct per-thread accesses above
+    auto kern = [] {
+        if constexpr (N >= 12)
+            return tps_kernel<kAlgo, N>;
+        else
+            return tps_kernel_staged<kAlgo, N>;
+    }();
+    constexpr size_t smem = (size_t)kTpsThreads * tps_thread_doubles(N) * sizeof(double);
+    int occ = 1;
+    cudaError_t ce = cached_occupancy(kern, kTpsThreads, smem, smem, &occ);
+    if (ce != cudaSuccess) return ce;
+    long long blocks = (batch + kTpsThreads - 1) / kTpsThreads;
+    const long long resident = (long long)sms * occ;
+    if (blocks > resident) blocks = resident;
+    kern<<<(unsigned)blocks, kTpsThreads, smem, st>>>(batch, a, l, e, p, k);
+    return cudaGetLastError();
+}
+template <int kAlgo>
+static cudaError_t launch_tps_algo(int n, long long batch, const double* a, double* l, double* e,
+                                   unsigned long long* p, int* k, int sms, cudaStream_t st)
+{
+    switch (n) {
+    case 9: return launch_tps_n<kAlgo, 9>(batch, a, l, e, p, k, sms, st);
+    case 10: return launch_tps_n<kAlgo, 10>(batch, a, l, e, p, k, sms, st);
+    case 11: return launch_tps_n<kAlgo, 11>(batch, a, l, e, p, k, sms, st);
+    case 12: return launch_tps_n<kAlgo, 12>(batch, a, l, e, p, k, sms, st);
+    case 13: return launch_tps_n<kAlgo, 13>(batch, a, l, e, p, k, sms, st);
+    case 14: return launch_tps_n<kAlgo, 14>(batch, a, l, e, p, k, sms, st);
+    case 15: return launch_tps_n<kAlgo, 15>(batch, a, l, e, p, k, sms, st);
+    case 16: return launch_tps_n<kAlgo, 16>(batch, a, l, e, p, k, sms, st);
+    default: return cudaErrorNotSupported;
+    }
+}
+static_assert(kTpsMaxN == 16, "launch_tps_algo lists the instantiations");
+
 static bool tpr_enabled()   // MODCHOL_TPR=0: the run-time-n kernels for every n <= 8 (A/B knob)
 {
     const char* v = getenv("MODCHOL_TPR");
@@ -67,6 +132,11 @@ static bool tpr_enabled()   // MODCHOL_TPR=0: the run-time-n kernels for every n
 cudaError_t launch_tpm_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
+    if (n > kTpmMaxN && n <= kTpsMaxN) {
+        if (algo == kSE90) return launch_tps_algo<kSE90>(n, batch, a, l, e, p, k, sms, st);
+        if (algo == kSE99) return launch_tps_algo<kSE99>(n, batch, a, l, e, p, k, sms, st);
+        return cudaErrorNotSupported;
+    }
     if (n < 1 || n > kTpmMaxN)
         return cudaErrorNotSupported;
     if (n <= kTprMaxN && tpr_enabled()) {

@@ -714,12 +714,114 @@ __device__ __forceinline__ void tpr_gmw(TprGmw<N>& s)
             l(i, q) = dadd(0.0, q == i ? dsqrt(s.d[q]) : dmul(l(i, q), dsqrt(s.d[q])));
 }
 
+// ---- direct global access of one thread to ITS matrix ------------------------------------------
+// The threads of a warp hold consecutive matrices, so one warp-wide access touches 32 different
+// sectors; every byte of a sector is consumed by the same thread within the next instructions
+// (L1 serves the rest of the sector), so DRAM sees each needed sector once -- and nothing has to be
+// staged, indexed or synchronised.  Only the lower triangle is read.  128-bit loads / 256-bit
+// stores where the row length and the base alignment allow.
+__device__ __forceinline__ void tp_stg_v4(double* p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// put(i, k, value) for every k <= i
+template <int N, typename F>
+__device__ __forceinline__ void tp_load_lower(const double* __restrict__ a, bool al16, F&& put)
+{
+    if (N % 2 == 0 && al16) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int k = 0; k <= i; k += 2) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(a + i * N + k));
+                put(i, k, v.x);
+                if (k + 1 <= i)
+                    put(i, k + 1, v.y);
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int k = 0; k <= i; ++k)
+                put(i, k, __ldg(a + i * N + k));
+    }
+}
+// the full row-major L: get(i, k) for k <= i, zero above the diagonal
+template <int N, typename F>
+__device__ __forceinline__ void tp_store_full(double* __restrict__ dst, bool al32, bool al16, F&& get)
+{
+    auto val = [&](int i, int k) { return k <= i ? get(i, k) : 0.0; };
+    if (N % 4 == 0 && al32) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int k = 0; k < N; k += 4)
+                tp_stg_v4(dst + i * N + k, val(i, k), val(i, k + 1), val(i, k + 2), val(i, k + 3));
+    } else if (N % 2 == 0 && al16) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int k = 0; k < N; k += 2)
+                *reinterpret_cast<double2*>(dst + i * N + k) = make_double2(val(i, k), val(i, k + 1));
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int k = 0; k < N; ++k)
+                dst[i * N + k] = val(i, k);
+    }
+}
+
+template <int kAlgo, int N>
+__global__ void __launch_bounds__(kTpmThreads)
+tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L,
+           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    constexpr int NN = N * N;
+    const bool al16 = (((size_t)A | (size_t)L) & 15) == 0, al32 = (((size_t)L) & 31) == 0;
+    const long long stride = (long long)gridDim.x * kTpmThreads;
+    for (long long b = (long long)blockIdx.x * kTpmThreads + threadIdx.x; b < batch; b += stride) {
+        const double* a = A + (size_t)b * NN;
+        int kstart = -1;
+        if constexpr (kAlgo == kGMW81) {
+            TprGmw<N> s;
+            tp_load_lower<N>(a, al16, [&](int i, int k, double v) { s.l(i, k) = v; });
+            tpr_gmw<N>(s);
+            if (L)   // gmw81.rs:119-123
+                tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return s.l(i, k); });
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (E) E[(size_t)b * N + s.p[i]] = s.e[i];   // gmw81.rs:127-131
+                if (P) P[(size_t)b * N + i] = (unsigned long long)s.p[i];
+            }
+        } else {
+            TprSe<N> s;
+            tp_load_lower<N>(a, al16, [&](int i, int k, double v) { s.l(i, k) = v; });
+            tpr_se<kAlgo, N>(s);
+            kstart = s.kstart;
+            if (L)   // se90.rs:169-173, se99.rs:189-192
+                tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return s.l(i, k); });
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (E) E[(size_t)b * N + s.p[i]] = s.e[i];   // se90.rs:174-178, se99.rs:194-198
+                if (P) P[(size_t)b * N + i] = (unsigned long long)s.p[i];
+            }
+        }
+        if (K)
+            K[b] = kstart;
+    }
+}
+
+// ---- the same kernel with the tile STAGED through shared memory: fully coalesced copies of a tile of
+// kTpmThreads matrices (word q of the tile at q + q / (N N) for even N: odd stride between the
+// threads' matrices), a barrier either side of the arithmetic.  Ahead of the direct accesses
+// wherever these are narrower than a sector's worth per thread and instruction (odd n, n = 4, 6).
 // doubles of shared memory per thread: the matrix (stride N N | 1), then e and p (stride N | 1)
 __host__ __device__ constexpr int tpr_thread_doubles(int n) { return tpm_mat_stride(n) + 2 * tpm_vec_stride(n); }
 
 template <int kAlgo, int N>
 __global__ void __launch_bounds__(kTpmThreads)
-tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L,
+tpr_kernel_staged(long long batch, const double* __restrict__ A, double* __restrict__ L,
            double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
 {
     extern __shared__ double sm[];
@@ -798,6 +900,336 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
         if (K && tid < cnt)
             K[t0 + tid] = kstart;
         __syncthreads();   // the tile's shared memory is free again
+    }
+}
+
+
+// ================================================================================================
+// 8 < n <= kTpsMaxN: still one thread per matrix, but the lower triangle no longer fits the
+// register file -- it lives in a thread-private range of SHARED memory (packed, T(n) doubles, odd
+// stride between threads: conflict free whenever the threads of a warp touch the same element),
+// together with g, e and p.  n is a compile-time constant; the O(n^2)-per-step trailing update is
+// instantiated per column (tps_update<N, J>), everything that is O(n) per step (pivot search,
+// exchange, column scaling, norms, bound updates) runs as ordinary loops over run-time indices, so
+// the code stays inside the instruction cache.  One warp per block (32 matrices per tile), no
+// block-wide barrier.
+// Sums of eight or more terms follow ndarray's unrolled_fold (eight partials, see common.cuh).
+// SE90 / SE99 only (GMW81 needs a second triangle per thread; it keeps the warp kernels).
+// ================================================================================================
+constexpr int kTpsMaxN = 16;
+constexpr int kTpsThreads = 32;
+__host__ __device__ constexpr int tps_thread_doubles(int n) { return (n * (n + 1) / 2 + 3 * n) | 1; }
+
+// ndarray `Array1::sum()` over len terms x(0) .. x(len-1)
+template <typename F>
+__device__ __forceinline__ double tps_nd_sum(int len, F x)
+{
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0, p5 = 0.0, p6 = 0.0, p7 = 0.0;
+    int i = 0;
+    for (; i + 8 <= len; i += 8) {
+        p0 = dadd(p0, x(i));
+        p1 = dadd(p1, x(i + 1));
+        p2 = dadd(p2, x(i + 2));
+        p3 = dadd(p3, x(i + 3));
+        p4 = dadd(p4, x(i + 4));
+        p5 = dadd(p5, x(i + 5));
+        p6 = dadd(p6, x(i + 6));
+        p7 = dadd(p7, x(i + 7));
+    }
+    double acc = 0.0;
+    acc = dadd(acc, dadd(p0, p4));
+    acc = dadd(acc, dadd(p1, p5));
+    acc = dadd(acc, dadd(p2, p6));
+    acc = dadd(acc, dadd(p3, p7));
+    for (; i < len; ++i)
+        acc = dadd(acc, x(i));
+    return acc;
+}
+
+__device__ __forceinline__ int tps_tri(int i) { return (i * (i + 1)) >> 1; }
+
+// symmetric exchange j <-> m (j < m) on the packed lower triangle: utils.rs:41-49 + :30-38
+__device__ __forceinline__ void tps_swap(double* l, int n, int j, int m)
+{
+    const int tj = tps_tri(j), tm = tps_tri(m);
+    auto sw = [&](int a, int b) {
+        const double t = l[a];
+        l[a] = l[b];
+        l[b] = t;
+    };
+    sw(tj + j, tm + m);
+    for (int k = 0; k < j; ++k)
+        sw(tj + k, tm + k);
+    for (int k = j + 1; k < m; ++k)
+        sw(tps_tri(k) + j, tm + k);
+    for (int k = m + 1; k < n; ++k) {
+        const int tk = tps_tri(k);
+        sw(tk + j, tk + m);
+    }
+}
+
+// se90.rs:84-93 == :142-151 == se99.rs:96-105 == :162-171 in two parts.  The column scaling
+// (one square root, n-j-1 divisions -- each a twenty-instruction sequence) is an ordinary loop
+// over the run-time column j: one copy in the instruction stream ...
+__device__ __forceinline__ void tps_scale_column(double* l, int n, int j)
+{
+    const int tj = tps_tri(j);
+    const double ljj = dsqrt(l[tj + j]);
+    l[tj + j] = ljj;
+#pragma unroll 4
+    for (int i = j + 1; i < n; ++i) {
+        const int a = tps_tri(i) + j;
+        l[a] = ddiv(l[a], ljj);
+    }
+}
+// ... and the O(n^2) trailing update is instantiated per column J: the scaled column in registers,
+// every trailing element one LDS + DMUL + DSUB + STS at a constant offset
+template <int N, int J>
+__device__ __forceinline__ void tps_update(double* l)
+{
+    double col[N];
+#pragma unroll
+    for (int i = J + 1; i < N; ++i)
+        col[i] = l[i * (i + 1) / 2 + J];
+#pragma unroll
+    for (int i = J + 1; i < N; ++i)
+#pragma unroll
+        for (int k = J + 1; k <= i; ++k)
+            l[i * (i + 1) / 2 + k] = dsub(l[i * (i + 1) / 2 + k], dmul(col[i], col[k]));
+}
+template <int N, int J>
+__device__ __forceinline__ void tps_eliminate_at(double* l, int j)
+{
+    if constexpr (J < N) {
+        if (j == J)
+            tps_update<N, J>(l);
+        else
+            tps_eliminate_at<N, J + 1>(l, j);
+    }
+}
+
+// SE90 / SE99 on the packed lower triangle at l; g, e, p: N doubles each.  Returns kstart.
+template <int kAlgo, int N>
+__device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p)
+{
+    double gamma = 0.0;   // se90.rs:55-57, se99.rs:54-56
+    for (int i = 0; i < N; ++i) {
+        e[i] = 0.0;
+        p[i] = (double)i;
+        g[i] = 0.0;
+        const double d = fabs(l[tps_tri(i) + i]);
+        if (d > gamma)
+            gamma = d;
+    }
+    const double taugamma = dmul(MODCHOL_TAU, gamma);
+    bool ph1 = true;
+    int kstart = -1;
+    double delta_prev = 0.0;
+    for (int j = 0; j < N; ++j) {
+        const int tj = tps_tri(j);
+        bool elim = false;
+        if (ph1) {   // phase 1: se90.rs:61-96, se99.rs:61-109
+            if (kAlgo == kSE99) {   // se99.rs:62-73
+                double dmax = -INFINITY, dmin = INFINITY;
+                for (int i = j; i < N; ++i) {
+                    const double x = l[tps_tri(i) + i];
+                    if (x > dmax) dmax = x;
+                    if (x < dmin) dmin = x;
+                }
+                if (dmax < taugamma || dmin < dmul(-MODCHOL_MU, dmax))
+                    ph1 = false;
+            }
+            if (ph1) {
+                int m = j;   // utils.rs:52-70
+                double best = l[tj + j];
+                for (int i = j + 1; i < N; ++i) {
+                    const double c = l[tps_tri(i) + i];
+                    if (c > best) {
+                        best = c;
+                        m = i;
+                    }
+                }
+                if (m != j) {   // se90.rs:63-68, se99.rs:76-81
+                    tps_swap(l, N, j, m);
+                    const double t = p[j];
+                    p[j] = p[m];
+                    p[m] = t;
+                }
+                double la = INFINITY;   // se90.rs:70-77, se99.rs:82-89
+                const double ljj = l[tj + j];
+                for (int i = j + 1; i < N; ++i) {
+                    const int ti = tps_tri(i);
+                    const double lij = l[ti + j];
+                    const double nv = dsub(l[ti + i], ddiv(dmul(lij, lij), ljj));
+                    if (nv < la)
+                        la = nv;
+                }
+                const double thresh = kAlgo == kSE99 ? dmul(-MODCHOL_MU, gamma) : taugamma;   // se99.rs:90 / se90.rs:78
+                if (la < thresh)
+                    ph1 = false;
+                else
+                    elim = true;
+            }
+            if (!ph1) {
+                kstart = j;   // phase 2 starts at this column
+                if (kAlgo == kSE99 && j == N - 1) {   // se99.rs:115-119
+                    const double ljj = l[tj + j];
+                    const double ej = tail1x1_e(ljj, gamma);
+                    e[j] = ej;
+                    l[tj + j] = dsqrt(dadd(ljj, ej));
+                } else if (kAlgo == kSE90 || j + 1 < N) {
+                    // lower Gershgorin bounds of the trailing block, se90.rs:105-110, se99.rs:125-130
+                    for (int i = j; i < N; ++i) {
+                        const int ti = tps_tri(i);
+                        const double s1 = tps_nd_sum(i - j, [&](int q) { return fabs(l[ti + j + q]); });
+                        const double s2 = tps_nd_sum(N - 1 - i, [&](int r) { return fabs(l[tps_tri(i + 1 + r) + i]); });
+                        g[i] = dsub(dsub(l[ti + i], s1), s2);
+                    }
+                }
+            }
+        }
+        if (!ph1 && j + 2 < N) {   // phase-2 step, se90.rs:113-152, se99.rs:133-172
+            int m = j;
+            double best = g[j];
+            for (int i = j + 1; i < N; ++i) {
+                const double c = g[i];
+                if (c > best) {
+                    best = c;
+                    m = i;
+                }
+            }
+            if (m != j) {
+                tps_swap(l, N, j, m);
+                double t = p[j];
+                p[j] = p[m];
+                p[m] = t;
+                t = g[j];
+                g[j] = g[m];
+                g[m] = t;
+            }
+            // se90.rs:124-131, se99.rs:144-151
+            const double normj = tps_nd_sum(N - 1 - j, [&](int r) { return fabs(l[tps_tri(j + 1 + r) + j]); });
+            double ljj = l[tj + j];
+            const double ej = phase2_e(ljj, normj, taugamma, delta_prev);
+            e[j] = ej;
+            if (ej > 0.0) {
+                ljj = dadd(ljj, ej);
+                l[tj + j] = ljj;
+                delta_prev = ej;
+            }
+            if (fabs(dsub(ljj, normj)) > MODCHOL_EPS) {   // se90.rs:134-139, se99.rs:154-159
+                const double t = dsub(1.0, ddiv(normj, ljj));
+                for (int i = j + 1; i < N; ++i)
+                    g[i] = dadd(g[i], dmul(fabs(l[tps_tri(i) + j]), t));
+            }
+            elim = true;
+        }
+        if (elim) {
+            tps_scale_column(l, N, j);
+            tps_eliminate_at<N, 0>(l, j);
+        }
+    }
+    if (!ph1 && (kAlgo == kSE90 || kstart + 1 < N)) {   // final 2x2: se90.rs:155-166, se99.rs:175-186
+        constexpr int A00 = (N - 2) * (N - 1) / 2 + (N - 2), A10 = (N - 1) * N / 2 + (N - 2), A11 = A10 + 1;
+        double lhi, llo;
+        const double off = l[A10];   // m[0,1] == m[1,0] (symmetric working matrix)
+        eigenvalues_2x2(l[A00], off, off, l[A11], lhi, llo);
+        const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
+        e[N - 2] = en;
+        e[N - 1] = en;
+        double a00 = l[A00], a11 = l[A11];
+        if (en > 0.0) {
+            a00 = dadd(a00, en);
+            a11 = dadd(a11, en);
+        }
+        const double l00 = dsqrt(a00);
+        l[A00] = l00;
+        const double l10 = ddiv(off, l00);
+        l[A10] = l10;
+        l[A11] = dsqrt(dsub(a11, dmul(l10, l10)));
+    }
+    return kstart;
+}
+
+template <int kAlgo, int N>
+__global__ void __launch_bounds__(kTpsThreads)
+tps_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L,
+           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    extern __shared__ double sm[];
+    constexpr int NN = N * N, T = N * (N + 1) / 2, S = tps_thread_doubles(N);
+    double* mine = sm + threadIdx.x * S;
+    double *g = mine + T, *e = g + N, *p = e + N;
+    const bool al16 = (((size_t)A | (size_t)L) & 15) == 0, al32 = (((size_t)L) & 31) == 0;
+    const long long stride = (long long)gridDim.x * kTpsThreads;
+    for (long long b = (long long)blockIdx.x * kTpsThreads + threadIdx.x; b < batch; b += stride) {
+        // in: the lower triangle straight from this thread's matrix (see tp_load_lower)
+        tp_load_lower<N>(A + (size_t)b * NN, al16, [&](int i, int k, double v) { mine[i * (i + 1) / 2 + k] = v; });
+        const int kstart = tps_se<kAlgo, N>(mine, g, e, p);
+        if (L)   // se90.rs:169-173, se99.rs:189-192
+            tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return mine[i * (i + 1) / 2 + k]; });
+        for (int i = 0; i < N; ++i) {   // se90.rs:174-178, se99.rs:194-198
+            const int pi = (int)p[i];
+            if (E) E[(size_t)b * N + pi] = e[i];
+            if (P) P[(size_t)b * N + i] = (unsigned long long)pi;
+        }
+        if (K)
+            K[b] = kstart;
+    }
+}
+
+// ---- staged variant: the warp copies its tile of 32 matrices with coalesced accesses (only the
+// lower triangle is fetched and kept); ahead of the direct accesses for n <= 11
+template <int kAlgo, int N>
+__global__ void __launch_bounds__(kTpsThreads)
+tps_kernel_staged(long long batch, const double* __restrict__ A, double* __restrict__ L,
+                  double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+{
+    extern __shared__ double sm[];
+    constexpr int NN = N * N, T = N * (N + 1) / 2, S = tps_thread_doubles(N);
+    const int lane = threadIdx.x;
+    double* mine = sm + lane * S;
+
+    for (long long t0 = (long long)blockIdx.x * kTpsThreads; t0 < batch; t0 += (long long)gridDim.x * kTpsThreads) {
+        const int cnt = (int)min((long long)kTpsThreads, batch - t0);
+        const int words = cnt * NN;
+        {
+            const double* src = A + (size_t)t0 * NN;
+            for (int q = lane; q < words; q += kTpsThreads) {
+                const int mat = q / NN, r = q - mat * NN, i = r / N, k = r - i * N;
+                if (k <= i)
+                    sm[mat * S + i * (i + 1) / 2 + k] = __ldg(src + q);
+            }
+        }
+        __syncwarp();
+        int kstart = -1;
+        if (lane < cnt) {
+            double *g = mine + T, *e = g + N, *p = e + N;
+            kstart = tps_se<kAlgo, N>(mine, g, e, p);
+            for (int i = 0; i < N; ++i)   // e in original order (se90.rs:174-178, se99.rs:194-198): through g
+                g[(int)p[i]] = e[i];
+        }
+        __syncwarp();
+        if (L) {   // L with its strict upper triangle zero (se90.rs:169-173, se99.rs:189-192)
+            double* dst = L + (size_t)t0 * NN;
+            for (int q = lane; q < words; q += kTpsThreads) {
+                const int mat = q / NN, r = q - mat * NN, i = r / N, k = r - i * N;
+                dst[q] = k <= i ? sm[mat * S + i * (i + 1) / 2 + k] : 0.0;
+            }
+        }
+        {
+            const int vwords = cnt * N;
+            for (int q = lane; q < vwords; q += kTpsThreads) {
+                const int mat = q / N, i = q - mat * N;
+                if (E)
+                    E[(size_t)t0 * N + q] = sm[mat * S + T + i];
+                if (P)
+                    P[(size_t)t0 * N + q] = (unsigned long long)sm[mat * S + T + 2 * N + i];
+            }
+        }
+        if (K && lane < cnt)
+            K[t0 + lane] = kstart;
+        __syncwarp();   // the tile's shared memory is free again
     }
 }
 

@@ -42,7 +42,7 @@ def test_version_and_kernel_classes():
     assert m.kernel_class("se90", 64) == "warp_smem"
     assert m.kernel_class("se99", 32, "fast") == "warp_smem" and m.kernel_class("gmw81", 64) == "warp_smem"
     assert m.kernel_class("gmw81", 65) == "cta_packed"
-    assert m.kernel_class("se99", 32, "strict") == "warp_smem" and m.kernel_class("se99", 16, "strict") == "warp_smem"
+    assert m.kernel_class("se99", 32, "strict") == "warp_smem" and m.kernel_class("se99", 16, "strict") == "thread"
     assert m.kernel_class("gmw81", 32) == "warp_smem" and m.kernel_class("gmw81", 3, "fast") == "thread"
     assert m.kernel_class("se99", 4096) == "unsupported"
 
