@@ -542,9 +542,18 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
         return rc;
     const DeviceCtx& c = g_ctx[dev];
     // every shared-memory warp class (n <= 64, both modes) carries its own fused solve
-    // (the thread-per-matrix class has no solve of its own: its sizes keep the fused warp kernels)
+    // (the thread-per-matrix class carries its own solve for n <= 8; for 8 < n <= 16 its factor
+    // kernel followed by the solve kernel is ahead of the fused warp kernels: SE99 n=16 STRICT 213
+    // against 196 M systems/s)
     const KernelClass cls = classify(algo, mode, n, c.smem_optin);
-    const bool fused = cls == kClsWarpSmem || cls == kClsThread;
+    if (cls == kClsThread && n <= kTpmMaxNHost) {
+        cudaError_t ce = launch_tpm_solve_kernel(algo, n, batch, a, l, e, p, k, b, x, nrhs, c.sms, st);
+        g_launches.fetch_add(1);
+        if (ce != cudaSuccess)
+            return fail(MODCHOL_ERR_CUDA, "fused factor+solve launch failed: %s", cudaGetErrorString(ce));
+        return MODCHOL_OK;
+    }
+    const bool fused = cls == kClsWarpSmem;
     if (fused) {
         cudaError_t ce = launch_wsm_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st, b, x, nrhs);
         g_launches.fetch_add(1);

@@ -27,14 +27,15 @@ static cudaError_t launch_tpm_algo(int n, long long batch, const double* a, doub
 // compile-time n, everything in registers (n <= kTprMaxN).  Direct per-thread global accesses
 // where one thread moves at least a sector's worth per instruction pair (n = 2, 8), the tile
 // staged through shared memory otherwise (measured: profiles/r02_thread_per_matrix.txt).
-template <int kAlgo, int N>
+template <int kAlgo, int N, bool kSolve>
 static cudaError_t launch_tpr_n(long long batch, const double* a, double* l, double* e,
-                                unsigned long long* p, int* k, int sms, cudaStream_t st)
+                                unsigned long long* p, int* k, int sms, cudaStream_t st,
+                                const double* rhs, double* x, int nrhs)
 {
     constexpr bool kDirect = N == 2 || N == 8;
     long long blocks = (batch + kTpmThreads - 1) / kTpmThreads;
     if constexpr (kDirect) {
-        auto kern = tpr_kernel<kAlgo, N>;
+        auto kern = tpr_kernel<kAlgo, N, kSolve>;
         // no shared memory: the whole carve-out goes to L1, which serves the rest of each sector a
         // thread has touched (queried once per device)
         static int occ_dev[64];
@@ -52,32 +53,33 @@ static cudaError_t launch_tpr_n(long long batch, const double* a, double* l, dou
         }
         const long long resident = (long long)sms * occ;
         if (blocks > resident) blocks = resident;
-        kern<<<(unsigned)blocks, kTpmThreads, 0, st>>>(batch, a, l, e, p, k);
+        kern<<<(unsigned)blocks, kTpmThreads, 0, st>>>(batch, a, l, e, p, k, rhs, x, nrhs);
     } else {
-        auto kern = tpr_kernel_staged<kAlgo, N>;
+        auto kern = tpr_kernel_staged<kAlgo, N, kSolve>;
         constexpr size_t smem = (size_t)kTpmThreads * tpr_thread_doubles(N) * sizeof(double);
         int occ = 1;
         cudaError_t ce = cached_occupancy(kern, kTpmThreads, smem, smem, &occ);
         if (ce != cudaSuccess) return ce;
         const long long resident = (long long)sms * occ;
         if (blocks > resident) blocks = resident;
-        kern<<<(unsigned)blocks, kTpmThreads, smem, st>>>(batch, a, l, e, p, k);
+        kern<<<(unsigned)blocks, kTpmThreads, smem, st>>>(batch, a, l, e, p, k, rhs, x, nrhs);
     }
     return cudaGetLastError();
 }
-template <int kAlgo>
+template <int kAlgo, bool kSolve>
 static cudaError_t launch_tpr_algo(int n, long long batch, const double* a, double* l, double* e,
-                                   unsigned long long* p, int* k, int sms, cudaStream_t st)
+                                   unsigned long long* p, int* k, int sms, cudaStream_t st,
+                                   const double* rhs, double* x, int nrhs)
 {
     switch (n) {
-    case 1: return launch_tpr_n<kAlgo, 1>(batch, a, l, e, p, k, sms, st);
-    case 2: return launch_tpr_n<kAlgo, 2>(batch, a, l, e, p, k, sms, st);
-    case 3: return launch_tpr_n<kAlgo, 3>(batch, a, l, e, p, k, sms, st);
-    case 4: return launch_tpr_n<kAlgo, 4>(batch, a, l, e, p, k, sms, st);
-    case 5: return launch_tpr_n<kAlgo, 5>(batch, a, l, e, p, k, sms, st);
-    case 6: return launch_tpr_n<kAlgo, 6>(batch, a, l, e, p, k, sms, st);
-    case 7: return launch_tpr_n<kAlgo, 7>(batch, a, l, e, p, k, sms, st);
-    case 8: return launch_tpr_n<kAlgo, 8>(batch, a, l, e, p, k, sms, st);
+    case 1: return launch_tpr_n<kAlgo, 1, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    case 2: return launch_tpr_n<kAlgo, 2, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    case 3: return launch_tpr_n<kAlgo, 3, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    case 4: return launch_tpr_n<kAlgo, 4, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    case 5: return launch_tpr_n<kAlgo, 5, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    case 6: return launch_tpr_n<kAlgo, 6, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    case 7: return launch_tpr_n<kAlgo, 7, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    case 8: return launch_tpr_n<kAlgo, 8, kSolve>(batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
     default: return cudaErrorNotSupported;
     }
 }
@@ -140,13 +142,26 @@ cudaError_t launch_tpm_kernel(int algo, int n, long long batch, const double* a,
     if (n < 1 || n > kTpmMaxN)
         return cudaErrorNotSupported;
     if (n <= kTprMaxN && tpr_enabled()) {
-        if (algo == kGMW81) return launch_tpr_algo<kGMW81>(n, batch, a, l, e, p, k, sms, st);
-        if (algo == kSE90) return launch_tpr_algo<kSE90>(n, batch, a, l, e, p, k, sms, st);
-        if (algo == kSE99) return launch_tpr_algo<kSE99>(n, batch, a, l, e, p, k, sms, st);
+        if (algo == kGMW81) return launch_tpr_algo<kGMW81, false>(n, batch, a, l, e, p, k, sms, st, nullptr, nullptr, 0);
+        if (algo == kSE90) return launch_tpr_algo<kSE90, false>(n, batch, a, l, e, p, k, sms, st, nullptr, nullptr, 0);
+        if (algo == kSE99) return launch_tpr_algo<kSE99, false>(n, batch, a, l, e, p, k, sms, st, nullptr, nullptr, 0);
     }
     if (algo == kGMW81) return launch_tpm_algo<kGMW81>(n, batch, a, l, e, p, k, sms, st);
     if (algo == kSE90) return launch_tpm_algo<kSE90>(n, batch, a, l, e, p, k, sms, st);
     if (algo == kSE99) return launch_tpm_algo<kSE99>(n, batch, a, l, e, p, k, sms, st);
+    return cudaErrorNotSupported;
+}
+
+// factorisation + solve in one kernel (n <= kTprMaxN): l, e, p, k may each be NULL
+cudaError_t launch_tpm_solve_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
+                                    unsigned long long* p, int* k, const double* rhs, double* x, int nrhs,
+                                    int sms, cudaStream_t st)
+{
+    if (n < 1 || n > kTprMaxN)
+        return cudaErrorNotSupported;
+    if (algo == kGMW81) return launch_tpr_algo<kGMW81, true>(n, batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    if (algo == kSE90) return launch_tpr_algo<kSE90, true>(n, batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
+    if (algo == kSE99) return launch_tpr_algo<kSE99, true>(n, batch, a, l, e, p, k, sms, st, rhs, x, nrhs);
     return cudaErrorNotSupported;
 }
 

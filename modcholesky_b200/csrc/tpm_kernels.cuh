@@ -714,6 +714,41 @@ __device__ __forceinline__ void tpr_gmw(TprGmw<N>& s)
             l(i, q) = dadd(0.0, q == i ? dsqrt(s.d[q]) : dmul(l(i, q), dsqrt(s.d[q])));
 }
 
+// The consumer step fused behind the factorisation: (A + E) x = rhs for nrhs right-hand sides of
+// this thread's matrix, L L^T (P x) = P rhs with L in registers (position order) and p.  x may alias rhs
+// (every entry of a right-hand side is read before the first is written).
+template <int N>
+__device__ __forceinline__ void tpr_solve(TprTri<N>& l, const int (&p)[N], const double* rhs, double* x, int nrhs)
+{
+    double rd[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        rd[i] = ddiv(1.0, l(i, i));
+    for (int r = 0; r < nrhs; ++r) {
+        double z[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            z[i] = rhs[(size_t)r * N + p[i]];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {   // L z = P rhs
+            z[j] = dmul(z[j], rd[j]);
+#pragma unroll
+            for (int i = j + 1; i < N; ++i)
+                z[i] = __fma_rn(-l(i, j), z[j], z[i]);
+        }
+#pragma unroll
+        for (int j = N - 1; j >= 0; --j) {   // L^T w = z
+            z[j] = dmul(z[j], rd[j]);
+#pragma unroll
+            for (int i = 0; i < j; ++i)
+                z[i] = __fma_rn(-l(j, i), z[j], z[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            x[(size_t)r * N + p[i]] = z[i];
+    }
+}
+
 // ---- direct global access of one thread to ITS matrix ------------------------------------------
 // The threads of a warp hold consecutive matrices, so one warp-wide access touches 32 different
 // sectors; every byte of a sector is consumed by the same thread within the next instructions
@@ -772,10 +807,11 @@ __device__ __forceinline__ void tp_store_full(double* __restrict__ dst, bool al3
     }
 }
 
-template <int kAlgo, int N>
+template <int kAlgo, int N, bool kSolve = false>
 __global__ void __launch_bounds__(kTpmThreads)
 tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L,
-           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
+           const double* Bm = nullptr, double* X = nullptr, int nrhs = 0)   // X may alias Bm
 {
     constexpr int NN = N * N;
     const bool al16 = (((size_t)A | (size_t)L) & 15) == 0, al32 = (((size_t)L) & 31) == 0;
@@ -794,6 +830,8 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
                 if (E) E[(size_t)b * N + s.p[i]] = s.e[i];   // gmw81.rs:127-131
                 if (P) P[(size_t)b * N + i] = (unsigned long long)s.p[i];
             }
+            if constexpr (kSolve)
+                tpr_solve<N>(s.l, s.p, Bm + (size_t)b * nrhs * N, X + (size_t)b * nrhs * N, nrhs);
         } else {
             TprSe<N> s;
             tp_load_lower<N>(a, al16, [&](int i, int k, double v) { s.l(i, k) = v; });
@@ -806,6 +844,8 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
                 if (E) E[(size_t)b * N + s.p[i]] = s.e[i];   // se90.rs:174-178, se99.rs:194-198
                 if (P) P[(size_t)b * N + i] = (unsigned long long)s.p[i];
             }
+            if constexpr (kSolve)
+                tpr_solve<N>(s.l, s.p, Bm + (size_t)b * nrhs * N, X + (size_t)b * nrhs * N, nrhs);
         }
         if (K)
             K[b] = kstart;
@@ -819,10 +859,11 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
 // doubles of shared memory per thread: the matrix (stride N N | 1), then e and p (stride N | 1)
 __host__ __device__ constexpr int tpr_thread_doubles(int n) { return tpm_mat_stride(n) + 2 * tpm_vec_stride(n); }
 
-template <int kAlgo, int N>
+template <int kAlgo, int N, bool kSolve = false>
 __global__ void __launch_bounds__(kTpmThreads)
 tpr_kernel_staged(long long batch, const double* __restrict__ A, double* __restrict__ L,
-           double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
+                  double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K,
+                  const double* Bm = nullptr, double* X = nullptr, int nrhs = 0)   // X may alias Bm
 {
     extern __shared__ double sm[];
     constexpr int NN = N * N, S = tpm_mat_stride(N), V = tpm_vec_stride(N);
@@ -861,6 +902,8 @@ tpr_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
                     eo[s.p[i]] = s.e[i];                                // gmw81.rs:127-131
                     po[i] = (unsigned long long)s.p[i];
                 }
+                if constexpr (kSolve)
+                    tpr_solve<N>(s.l, s.p, Bm + (size_t)(t0 + tid) * nrhs * N, X + (size_t)(t0 + tid) * nrhs * N, nrhs);
             } else {
                 TprSe<N> s;
 #pragma unroll
@@ -878,6 +921,8 @@ tpr_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
                     eo[s.p[i]] = s.e[i];                                // se90.rs:174-178, se99.rs:194-198
                     po[i] = (unsigned long long)s.p[i];
                 }
+                if constexpr (kSolve)
+                    tpr_solve<N>(s.l, s.p, Bm + (size_t)(t0 + tid) * nrhs * N, X + (size_t)(t0 + tid) * nrhs * N, nrhs);
             }
         }
         __syncthreads();

@@ -143,6 +143,9 @@ constexpr int kTpmMaxNHost = 8;    // registers / run-time n, all three algorith
 constexpr int kTpsMaxNHost = 16;   // triangle in thread-private shared memory, SE90 / SE99
 cudaError_t launch_tpm_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st);
+cudaError_t launch_tpm_solve_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
+                                    unsigned long long* p, int* k, const double* rhs, double* x, int nrhs,
+                                    int sms, cudaStream_t st);
 inline bool tpm_kernel_available(int algo, int n)
 {
     return algo >= 0 && algo <= 2 && n >= 1 && (n <= kTpmMaxNHost || (algo != 0 && n <= kTpsMaxNHost));

@@ -23,7 +23,7 @@ def timed(fn, reps=5):
     return sorted(ts)[len(ts) // 2]
 
 
-for algo, n, batch in (("se99", 32, 1 << 19), ("se99", 16, 1 << 20), ("se90", 64, 100000), ("gmw81", 32, 1 << 19)):
+for algo, n, batch in (("se99", 4, 1 << 22), ("se99", 8, 1 << 20), ("se99", 32, 1 << 19), ("se99", 16, 1 << 20), ("se90", 64, 100000), ("gmw81", 32, 1 << 19)):
     a = gen("uniform", batch, n)
     b = torch.randn((batch, n), dtype=torch.float64, device="cuda")
     for mode in ("strict", "fast"):
