@@ -241,17 +241,17 @@ int cta_ld(int n) { return (n & 1) ? n : n + 1; }
 
 // largest n served by the thread-per-matrix kernels by default (MODCHOL_TPM_MAX / MODCHOL_TPS_MAX,
 // tuning knobs read per call; 0 switches them off)
-int tpm_max_n(int n, int mode)
+int tpm_max_n(int n, int mode, int algo)
 {
     if (n <= kTpmMaxNHost) {
         const char* e = getenv("MODCHOL_TPM_MAX");
         return e ? atoi(e) : 8;   // measured: ahead of the warp kernels at every n <= 8, both modes
     }
-    // 8 < n <= 16 (SE90 / SE99, triangle in shared memory): ahead of the implicit-pivoting FAST
-    // kernels up to n = 10 and of the position-ordered STRICT kernels at every n <= 16
+    // 8 < n <= 16 (triangle in shared memory): ahead of the implicit-pivoting FAST kernels up to
+    // n = 10 (GMW81: 9) and of the position-ordered STRICT kernels at every n <= 16
     // (profiles/r02_thread_per_matrix.txt)
     const char* e = getenv("MODCHOL_TPS_MAX");
-    return e ? atoi(e) : (mode == MODCHOL_MODE_FAST ? 10 : 16);
+    return e ? atoi(e) : (mode == MODCHOL_MODE_FAST ? (algo == MODCHOL_GMW81 ? 9 : 10) : 16);
 }
 
 // smallest n served by the blocked large-n kernels (MODCHOL_BSM_MIN, tuning knob)
@@ -283,7 +283,7 @@ KernelClass classify(int algo, int mode, int n, int smem_optin)
     // modes for all but a few (n <= 8, STRICT, mixed-phase) cases, and it is the only warp-level
     // kernel for 32 < n <= 64 -- it is the default; the register family stays selectable.
     const bool auto_wsm = wsm_ok;
-    if (tpm_kernel_available(algo, n) && (pref == 3 || (pref == 0 && n <= tpm_max_n(n, mode))))
+    if (tpm_kernel_available(algo, n) && (pref == 3 || (pref == 0 && n <= tpm_max_n(n, mode, algo))))
         return kClsThread;
     if (wsm_ok && (pref == 2 || (pref == 0 && auto_wsm) || !reg_ok))
         return kClsWarpSmem;

@@ -85,7 +85,7 @@ static cudaError_t launch_tpr_algo(int n, long long batch, const double* a, doub
 }
 static_assert(kTprMaxN == 8, "launch_tpr_algo lists the instantiations");
 
-// 8 < n <= kTpsMaxN, SE90 / SE99: compile-time n, the triangle in thread-private shared memory
+// 8 < n <= kTpsMaxN: compile-time n, the triangle in thread-private shared memory
 template <int kAlgo, int N>
 static cudaError_t launch_tps_n(long long batch, const double* a, double* l, double* e,
                                 unsigned long long* p, int* k, int sms, cudaStream_t st)
@@ -97,7 +97,7 @@ static cudaError_t launch_tps_n(long long batch, const double* a, double* l, dou
         else
             return tps_kernel_staged<kAlgo, N>;
     }();
-    constexpr size_t smem = (size_t)kTpsThreads * tps_thread_doubles(N) * sizeof(double);
+    constexpr size_t smem = (size_t)kTpsThreads * tps_thread_doubles(N, kAlgo) * sizeof(double);
     int occ = 1;
     cudaError_t ce = cached_occupancy(kern, kTpsThreads, smem, smem, &occ);
     if (ce != cudaSuccess) return ce;
@@ -135,6 +135,7 @@ cudaError_t launch_tpm_kernel(int algo, int n, long long batch, const double* a,
                               unsigned long long* p, int* k, int sms, cudaStream_t st)
 {
     if (n > kTpmMaxN && n <= kTpsMaxN) {
+        if (algo == kGMW81) return launch_tps_algo<kGMW81>(n, batch, a, l, e, p, k, sms, st);
         if (algo == kSE90) return launch_tps_algo<kSE90>(n, batch, a, l, e, p, k, sms, st);
         if (algo == kSE99) return launch_tps_algo<kSE99>(n, batch, a, l, e, p, k, sms, st);
         return cudaErrorNotSupported;

@@ -959,11 +959,11 @@ tpr_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
 // the code stays inside the instruction cache.  One warp per block (32 matrices per tile), no
 // block-wide barrier.
 // Sums of eight or more terms follow ndarray's unrolled_fold (eight partials, see common.cuh).
-// SE90 / SE99 only (GMW81 needs a second triangle per thread; it keeps the warp kernels).
+// GMW81 shares one triangle between the reference's l and c (tps_gmw below).
 // ================================================================================================
 constexpr int kTpsMaxN = 16;
 constexpr int kTpsThreads = 32;
-__host__ __device__ constexpr int tps_thread_doubles(int n) { return (n * (n + 1) / 2 + 3 * n) | 1; }
+__host__ __device__ constexpr int tps_thread_doubles(int n, int algo = kSE99) { return (n * (n + 1) / 2 + (algo == kGMW81 ? 5 : 3) * n) | 1; }
 
 // ndarray `Array1::sum()` over len terms x(0) .. x(len-1)
 template <typename F>
@@ -1196,22 +1196,149 @@ __device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p
     return kstart;
 }
 
+// ---- GMW81 for 8 < n <= kTpsMaxN (gmw81.rs:39-134) on ONE triangle ------------------------------
+// The reference keeps two matrices, l (a clone of A that turns into the unit-lower factor) and c.
+// Per thread they share one packed triangle W: W(i, s), s < i, holds the (permuted) a_is until
+// column s is formed at step s, c_is from then on, and l_is = c_is / d_s once row i has been the
+// pivot row (step i: the quotients go through the buffer lrow while the dot products of the step
+// still need c_js).  The diagonal of W keeps a_ii (gmw81.rs:83-85 rebuilds c_jj from it); the
+// running diagonal c_ii that the pivot search and gmw81.rs:104-109 use lives in cd.
+// dot_J = sum_{s<J} lrow[s] * W(i, s) in ndarray's order, lrow in registers, J a compile-time constant
+template <int N, int J>
+__device__ __forceinline__ void tps_gmw_column(double* w, const double* lrow_s)
+{
+    double lr[J > 0 ? J : 1];
+#pragma unroll
+    for (int s = 0; s < J; ++s)
+        lr[s] = lrow_s[s];
+    for (int i = J; i < N; ++i) {
+        double* wi = w + tps_tri(i);
+        double acc = 0.0;
+        if constexpr (J >= 8) {
+            double pp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                pp[u] = 0.0;
+#pragma unroll
+            for (int s = 0; s < (J / 8) * 8; ++s)
+                pp[s % 8] = dadd(pp[s % 8], dmul(lr[s], wi[s]));
+            acc = dadd(acc, dadd(pp[0], pp[4]));
+            acc = dadd(acc, dadd(pp[1], pp[5]));
+            acc = dadd(acc, dadd(pp[2], pp[6]));
+            acc = dadd(acc, dadd(pp[3], pp[7]));
+        }
+#pragma unroll
+        for (int s = (J / 8) * 8; s < J; ++s)
+            acc = dadd(acc, dmul(lr[s], wi[s]));
+        wi[J] = dsub(wi[J], acc);   // gmw81.rs:83-85: c_iJ = l_iJ - sum
+    }
+}
+template <int N, int J>
+__device__ __forceinline__ void tps_gmw_column_at(double* w, const double* lrow_s, int j)
+{
+    if constexpr (J < N) {
+        if (j == J)
+            tps_gmw_column<N, J>(w, lrow_s);
+        else
+            tps_gmw_column_at<N, J + 1>(w, lrow_s, j);
+    }
+}
+
+// w: packed triangle (A's lower triangle on entry, L on exit); lrow, cd, d, e, p: N doubles each
+template <int N>
+__device__ __forceinline__ void tps_gmw(double* w, double* lrow, double* cd, double* d, double* e, double* p)
+{
+    double diag_max = 0.0, off_max = 0.0;   // gmw81.rs:49-58 (the upper triangle mirrors the lower)
+    for (int i = 0; i < N; ++i) {
+        const int ti = tps_tri(i);
+        e[i] = 0.0;
+        d[i] = 0.0;
+        p[i] = (double)i;
+        cd[i] = w[ti + i];   // gmw81.rs:66-68
+        const double v = fabs(w[ti + i]);
+        if (v > diag_max) diag_max = v;
+        for (int q = 0; q < i; ++q) {
+            const double o = fabs(w[ti + q]);
+            if (o > off_max) off_max = o;
+        }
+    }
+    const double nf = (double)N;
+    const double delta = dmul(MODCHOL_EPS, fmax(1.0, dadd(diag_max, off_max)));   // gmw81.rs:60
+    const double beta = dsqrt(fmax(fmax(diag_max, ddiv(off_max, dsqrt(dsub(dmul(nf, nf), 1.0)))), MODCHOL_EPS));   // :61-64
+    for (int j = 0; j < N; ++j) {
+        const int tj = tps_tri(j);
+        int m = j;   // utils.rs:73-91 on the running diagonal (gmw81.rs:71-78)
+        double best = fabs(cd[j]);
+        for (int i = j + 1; i < N; ++i) {
+            const double v = fabs(cd[i]);
+            if (v > best) {
+                best = v;
+                m = i;
+            }
+        }
+        if (m != j) {
+            tps_swap(w, N, j, m);
+            double t = p[j];
+            p[j] = p[m];
+            p[m] = t;
+            t = cd[j];
+            cd[j] = cd[m];
+            cd[m] = t;
+        }
+        for (int s = 0; s < j; ++s)   // gmw81.rs:79-81
+            lrow[s] = ddiv(w[tj + s], d[s]);
+        tps_gmw_column_at<N, 0>(w, lrow, j);   // gmw81.rs:83-85 for i = j .. n-1
+        for (int s = 0; s < j; ++s)   // row j of the factor is final
+            w[tj + s] = lrow[s];
+        double theta = 0.0;   // gmw81.rs:87-100
+        for (int i = j + 1; i < N; ++i) {
+            const double v = fabs(w[tps_tri(i) + j]);
+            if (v > theta)
+                theta = v;
+        }
+        const double tb = ddiv(theta, beta);
+        const double cjj = w[tj + j];
+        const double dj = fmax(fmax(fabs(cjj), dmul(tb, tb)), delta);   // gmw81.rs:102
+        d[j] = dj;
+#pragma unroll 4
+        for (int i = j + 1; i < N; ++i) {   // gmw81.rs:104-109
+            const double cij = w[tps_tri(i) + j];
+            cd[i] = dsub(cd[i], ddiv(dmul(cij, cij), dj));
+        }
+        e[j] = dsub(dj, cjj);   // gmw81.rs:110
+    }
+    // gmw81.rs:112-125: l . diag(sqrt(d)) with a unit diagonal; the dense product's accumulation
+    // from 0.0 turns a -0 into +0
+    for (int q = 0; q < N; ++q)
+        lrow[q] = dsqrt(d[q]);
+    for (int i = 0; i < N; ++i) {
+        const int ti = tps_tri(i);
+        for (int q = 0; q < i; ++q)
+            w[ti + q] = dadd(0.0, dmul(w[ti + q], lrow[q]));
+        w[ti + i] = dadd(0.0, lrow[i]);
+    }
+}
+
 template <int kAlgo, int N>
 __global__ void __launch_bounds__(kTpsThreads)
 tps_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L,
            double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
 {
     extern __shared__ double sm[];
-    constexpr int NN = N * N, T = N * (N + 1) / 2, S = tps_thread_doubles(N);
+    constexpr int NN = N * N, T = N * (N + 1) / 2, S = tps_thread_doubles(N, kAlgo);
     double* mine = sm + threadIdx.x * S;
-    double *g = mine + T, *e = g + N, *p = e + N;
+    double *g = mine + T, *e = g + N, *p = e + N;   // (GMW81: g is d; lrow and cd follow p)
     const bool al16 = (((size_t)A | (size_t)L) & 15) == 0, al32 = (((size_t)L) & 31) == 0;
     const long long stride = (long long)gridDim.x * kTpsThreads;
     for (long long b = (long long)blockIdx.x * kTpsThreads + threadIdx.x; b < batch; b += stride) {
         // in: the lower triangle straight from this thread's matrix (see tp_load_lower)
         tp_load_lower<N>(A + (size_t)b * NN, al16, [&](int i, int k, double v) { mine[i * (i + 1) / 2 + k] = v; });
-        const int kstart = tps_se<kAlgo, N>(mine, g, e, p);
-        if (L)   // se90.rs:169-173, se99.rs:189-192
+        int kstart = -1;
+        if constexpr (kAlgo == kGMW81)
+            tps_gmw<N>(mine, p + N, p + 2 * N, g, e, p);
+        else
+            kstart = tps_se<kAlgo, N>(mine, g, e, p);
+        if (L)   // se90.rs:169-173, se99.rs:189-192, gmw81.rs:119-123
             tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return mine[i * (i + 1) / 2 + k]; });
         for (int i = 0; i < N; ++i) {   // se90.rs:174-178, se99.rs:194-198
             const int pi = (int)p[i];
@@ -1231,7 +1358,7 @@ tps_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
                   double* __restrict__ E, unsigned long long* __restrict__ P, int* __restrict__ K)
 {
     extern __shared__ double sm[];
-    constexpr int NN = N * N, T = N * (N + 1) / 2, S = tps_thread_doubles(N);
+    constexpr int NN = N * N, T = N * (N + 1) / 2, S = tps_thread_doubles(N, kAlgo);
     const int lane = threadIdx.x;
     double* mine = sm + lane * S;
 
@@ -1250,7 +1377,10 @@ tps_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
         int kstart = -1;
         if (lane < cnt) {
             double *g = mine + T, *e = g + N, *p = e + N;
-            kstart = tps_se<kAlgo, N>(mine, g, e, p);
+            if constexpr (kAlgo == kGMW81)
+                tps_gmw<N>(mine, p + N, p + 2 * N, g, e, p);
+            else
+                kstart = tps_se<kAlgo, N>(mine, g, e, p);
             for (int i = 0; i < N; ++i)   // e in original order (se90.rs:174-178, se99.rs:194-198): through g
                 g[(int)p[i]] = e[i];
         }

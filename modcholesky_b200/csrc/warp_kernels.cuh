@@ -138,9 +138,9 @@ inline cudaError_t launch_lwm_kernel(int algo, int n, long long batch, const dou
 }
 
 // thread-per-matrix kernels (tpm_kernels.cuh), both modes (the reference's arithmetic element for
-// element), n <= 8 (SE90 / SE99: n <= 16); defined in tpm_inst.cu
+// element), n <= 16; defined in tpm_inst.cu
 constexpr int kTpmMaxNHost = 8;    // registers / run-time n, all three algorithms
-constexpr int kTpsMaxNHost = 16;   // triangle in thread-private shared memory, SE90 / SE99
+constexpr int kTpsMaxNHost = 16;   // triangle in thread-private shared memory
 cudaError_t launch_tpm_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
                               unsigned long long* p, int* k, int sms, cudaStream_t st);
 cudaError_t launch_tpm_solve_kernel(int algo, int n, long long batch, const double* a, double* l, double* e,
@@ -148,7 +148,7 @@ cudaError_t launch_tpm_solve_kernel(int algo, int n, long long batch, const doub
                                     int sms, cudaStream_t st);
 inline bool tpm_kernel_available(int algo, int n)
 {
-    return algo >= 0 && algo <= 2 && n >= 1 && (n <= kTpmMaxNHost || (algo != 0 && n <= kTpsMaxNHost));
+    return algo >= 0 && algo <= 2 && n >= 1 && n <= kTpsMaxNHost;
 }
 
 inline cudaError_t launch_warp_kernel(int algo, int mode, int n, long long batch, const double* a,

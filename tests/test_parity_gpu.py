@@ -192,9 +192,6 @@ def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
     prev = m.set_small_kernel_family("tpm")
     try:
         for algo in ALGOS:
-            if n > 8 and algo == "gmw81":   # 8 < n <= 16: SE90 / SE99 only
-                assert m.kernel_class(algo, n, "fast") != "thread"
-                continue
             for b, fam in ((1, "uniform"), (37, "wishart"), (128, "pd"), (129, "ties"), (1000, "uniform"),
                            (515, "bench"), (300, "wishart")):
                 if fam == "bench" and n < 3:
@@ -206,8 +203,9 @@ def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
                     _assert_bit_exact(f"tpm {algo} n={n} {fam} b={b} {mode}", _gpu(torch, algo, a, mode), ref)
     finally:
         m.set_small_kernel_family(prev)
-    # the default dispatch: n <= 8 always; SE90 / SE99 up to n = 10 (FAST) and n = 16 (STRICT)
-    assert m.kernel_class("se99", 8, "fast") == "thread" and m.kernel_class("gmw81", 9, "fast") == "warp_smem"
+    # the default dispatch: n <= 8 always; up to n = 10 (GMW81: 9) in FAST and n = 16 in STRICT mode
+    assert m.kernel_class("se99", 8, "fast") == "thread" and m.kernel_class("gmw81", 9, "fast") == "thread"
+    assert m.kernel_class("gmw81", 10, "fast") == "warp_smem" and m.kernel_class("gmw81", 16, "strict") == "thread"
     assert m.kernel_class("se99", 10, "fast") == "thread" and m.kernel_class("se99", 11, "fast") == "warp_smem"
     assert m.kernel_class("se90", 16, "strict") == "thread" and m.kernel_class("se90", 17, "strict") == "warp_smem"
 
