@@ -239,6 +239,8 @@ int small_kernel_pref()
 
 int cta_ld(int n) { return (n & 1) ? n : n + 1; }
 
+constexpr long long kThreadMinBatch = 512;   // below: the warp kernels (factor_device)
+
 // largest n served by the thread-per-matrix kernels by default (MODCHOL_TPM_MAX / MODCHOL_TPS_MAX,
 // tuning knobs read per call; 0 switches them off)
 int tpm_max_n(int n, int mode, int algo)
@@ -247,11 +249,12 @@ int tpm_max_n(int n, int mode, int algo)
         const char* e = getenv("MODCHOL_TPM_MAX");
         return e ? atoi(e) : 8;   // measured: ahead of the warp kernels at every n <= 8, both modes
     }
-    // 8 < n <= 16 (triangle in shared memory): ahead of the implicit-pivoting FAST kernels up to
-    // n = 10 (GMW81: 9) and of the position-ordered STRICT kernels at every n <= 16
-    // (profiles/r02_thread_per_matrix.txt)
+    // 8 < n <= 16 (triangle in shared memory): ahead of the position-ordered STRICT kernels at
+    // every n <= 16; against the implicit-pivoting FAST kernels ahead up to n = 10 (GMW81: 9), level
+    // at n = 11, 12 on symmetric-uniform input and 25 % ahead on the reference's bench family
+    // (Q D Q^T, phase 1) at n = 12 -- SE90 / SE99 take it up to 12 (profiles/r02_thread_per_matrix.txt)
     const char* e = getenv("MODCHOL_TPS_MAX");
-    return e ? atoi(e) : (mode == MODCHOL_MODE_FAST ? (algo == MODCHOL_GMW81 ? 9 : 10) : 16);
+    return e ? atoi(e) : (mode == MODCHOL_MODE_FAST ? (algo == MODCHOL_GMW81 ? 9 : 12) : 16);
 }
 
 // smallest n served by the blocked large-n kernels (MODCHOL_BSM_MIN, tuning knob)
@@ -337,7 +340,11 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
     if (rc)
         return rc;
     const DeviceCtx& c = g_ctx[dev];
-    const KernelClass cls = classify(algo, mode, n, c.smem_optin);
+    KernelClass cls = classify(algo, mode, n, c.smem_optin);
+    // one thread per matrix needs a batch to fill the machine: a handful of matrices (the trait
+    // call on one Array2) is served faster by a warp per matrix (12 x 12: 21 against 27 us)
+    if (cls == kClsThread && batch < kThreadMinBatch && small_kernel_pref() != 3)
+        cls = kClsWarpSmem;
     if (cls == kClsWarp) {
         cudaError_t ce = launch_warp_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st);
         g_launches.fetch_add(1);
@@ -545,7 +552,9 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
     // (the thread-per-matrix class carries its own solve for n <= 8; for 8 < n <= 16 its factor
     // kernel followed by the solve kernel is ahead of the fused warp kernels: SE99 n=16 STRICT 213
     // against 196 M systems/s)
-    const KernelClass cls = classify(algo, mode, n, c.smem_optin);
+    KernelClass cls = classify(algo, mode, n, c.smem_optin);
+    if (cls == kClsThread && batch < kThreadMinBatch && small_kernel_pref() != 3)
+        cls = kClsWarpSmem;
     if (cls == kClsThread && n <= kTpmMaxNHost) {
         cudaError_t ce = launch_tpm_solve_kernel(algo, n, batch, a, l, e, p, k, b, x, nrhs, c.sms, st);
         g_launches.fetch_add(1);
