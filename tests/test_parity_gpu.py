@@ -429,16 +429,20 @@ def test_eight_byte_aligned_buffers(oracle, torch_cuda):
     import ctypes
     from modcholesky_b200 import _lib
     torch = torch_cuda
-    for algo, n, b in (("se99", 32, 300), ("se90", 16, 300), ("gmw81", 24, 200), ("se99", 64, 50)):
+    # (the last five cases reach the thread-per-matrix kernels, whose direct accesses are 128-bit
+    # loads and 256-bit stores when the bases allow: off = 2 is 16- but not 32-byte aligned)
+    for algo, n, b, off in (("se99", 32, 300, 1), ("se90", 16, 300, 1), ("gmw81", 24, 200, 1), ("se99", 64, 50, 1),
+                            ("se99", 8, 700, 1), ("se99", 8, 700, 2), ("gmw81", 2, 600, 1), ("se90", 12, 600, 2),
+                            ("gmw81", 16, 600, 1)):
         a = matgen.make("uniform", 70 + n, b, n)
         ref = oracle.factor_batched(algo, a)
         for mode in ("strict", "fast"):
-            pad_a = torch.empty(b * n * n + 1, dtype=torch.float64, device="cuda")
-            pad_l = torch.empty(b * n * n + 1, dtype=torch.float64, device="cuda")
+            pad_a = torch.empty(b * n * n + off, dtype=torch.float64, device="cuda")
+            pad_l = torch.empty(b * n * n + off, dtype=torch.float64, device="cuda")
             pad_e = torch.empty(b * n + 1, dtype=torch.float64, device="cuda")
             pad_p = torch.empty(b * n + 1, dtype=torch.int64, device="cuda")
-            av, lv, evv, pv = pad_a[1:], pad_l[1:], pad_e[1:], pad_p[1:]
-            assert lv.data_ptr() % 16 == 8
+            av, lv, evv, pv = pad_a[off:], pad_l[off:], pad_e[1:], pad_p[1:]
+            assert lv.data_ptr() % 32 == 8 * off
             av.copy_(torch.from_numpy(a).reshape(-1))
             rc = _lib.lib().modchol_factor_batched_f64(
                 _lib.algo_id(algo), _lib.mode_id(mode), b, n, av.data_ptr(), lv.data_ptr(), evv.data_ptr(),
