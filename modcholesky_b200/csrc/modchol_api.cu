@@ -250,11 +250,11 @@ int tpm_max_n(int n, int mode, int algo)
         return e ? atoi(e) : 8;   // measured: ahead of the warp kernels at every n <= 8, both modes
     }
     // 8 < n <= 16 (triangle in shared memory): ahead of the position-ordered STRICT kernels at
-    // every n <= 16; against the implicit-pivoting FAST kernels ahead up to n = 10 (GMW81: 9), level
-    // at n = 11, 12 on symmetric-uniform input and 25 % ahead on the reference's bench family
-    // (Q D Q^T, phase 1) at n = 12 -- SE90 / SE99 take it up to 12 (profiles/r02_thread_per_matrix.txt)
+    // every n <= 16; against the implicit-pivoting FAST kernels ahead up to n = 12 (SE99: 602
+    // against 567 M/s on symmetric-uniform input, 608 against 423 on the reference's bench family)
+    // and up to n = 10 for GMW81 (profiles/r02_thread_per_matrix.txt)
     const char* e = getenv("MODCHOL_TPS_MAX");
-    return e ? atoi(e) : (mode == MODCHOL_MODE_FAST ? (algo == MODCHOL_GMW81 ? 9 : 12) : 16);
+    return e ? atoi(e) : (mode == MODCHOL_MODE_FAST ? (algo == MODCHOL_GMW81 ? 10 : 12) : 16);
 }
 
 // smallest n served by the blocked large-n kernels (MODCHOL_BSM_MIN, tuning knob)

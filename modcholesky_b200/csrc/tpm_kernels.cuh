@@ -963,7 +963,20 @@ tpr_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
 // ================================================================================================
 constexpr int kTpsMaxN = 16;
 constexpr int kTpsThreads = 32;
-__host__ __device__ constexpr int tps_thread_doubles(int n, int algo = kSE99) { return (n * (n + 1) / 2 + (algo == kGMW81 ? 5 : 3) * n) | 1; }
+// per thread: the triangle, then SE90 / SE99: one vector shared by g (positions not yet eliminated)
+// and e (positions already eliminated); GMW81: lrow, d and one vector shared by the running
+// diagonal and e.  The permutation is sixteen 4-bit fields of one register.
+__host__ __device__ constexpr int tps_thread_doubles(int n, int algo = kSE99) { return (n * (n + 1) / 2 + (algo == kGMW81 ? 3 : 1) * n) | 1; }
+
+struct TpsPerm {
+    unsigned long long v = 0xFEDCBA9876543210ull;   // p[i] = i
+    __device__ __forceinline__ int get(int i) const { return (int)((v >> (4 * i)) & 15ull); }
+    __device__ __forceinline__ void swap(int j, int m)
+    {
+        const unsigned long long x = (unsigned long long)(get(j) ^ get(m));
+        v ^= (x << (4 * j)) | (x << (4 * m));
+    }
+};
 
 // ndarray `Array1::sum()` over len terms x(0) .. x(len-1)
 template <typename F>
@@ -1055,13 +1068,11 @@ __device__ __forceinline__ void tps_eliminate_at(double* l, int j)
 
 // SE90 / SE99 on the packed lower triangle at l; g, e, p: N doubles each.  Returns kstart.
 template <int kAlgo, int N>
-__device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p)
+__device__ __forceinline__ int tps_se(double* l, double* g, TpsPerm& p)
 {
     double gamma = 0.0;   // se90.rs:55-57, se99.rs:54-56
     for (int i = 0; i < N; ++i) {
-        e[i] = 0.0;
-        p[i] = (double)i;
-        g[i] = 0.0;
+        g[i] = 0.0;   // e of a column that phase 1 eliminates
         const double d = fabs(l[tps_tri(i) + i]);
         if (d > gamma)
             gamma = d;
@@ -1096,9 +1107,7 @@ __device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p
                 }
                 if (m != j) {   // se90.rs:63-68, se99.rs:76-81
                     tps_swap(l, N, j, m);
-                    const double t = p[j];
-                    p[j] = p[m];
-                    p[m] = t;
+                    p.swap(j, m);
                 }
                 double la = INFINITY;   // se90.rs:70-77, se99.rs:82-89
                 const double ljj = l[tj + j];
@@ -1120,7 +1129,7 @@ __device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p
                 if (kAlgo == kSE99 && j == N - 1) {   // se99.rs:115-119
                     const double ljj = l[tj + j];
                     const double ej = tail1x1_e(ljj, gamma);
-                    e[j] = ej;
+                    g[j] = ej;
                     l[tj + j] = dsqrt(dadd(ljj, ej));
                 } else if (kAlgo == kSE90 || j + 1 < N) {
                     // lower Gershgorin bounds of the trailing block, se90.rs:105-110, se99.rs:125-130
@@ -1145,10 +1154,8 @@ __device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p
             }
             if (m != j) {
                 tps_swap(l, N, j, m);
-                double t = p[j];
-                p[j] = p[m];
-                p[m] = t;
-                t = g[j];
+                p.swap(j, m);
+                const double t = g[j];
                 g[j] = g[m];
                 g[m] = t;
             }
@@ -1156,7 +1163,7 @@ __device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p
             const double normj = tps_nd_sum(N - 1 - j, [&](int r) { return fabs(l[tps_tri(j + 1 + r) + j]); });
             double ljj = l[tj + j];
             const double ej = phase2_e(ljj, normj, taugamma, delta_prev);
-            e[j] = ej;
+            g[j] = ej;   // the bound of position j is dead: its slot takes e_j
             if (ej > 0.0) {
                 ljj = dadd(ljj, ej);
                 l[tj + j] = ljj;
@@ -1180,8 +1187,8 @@ __device__ __forceinline__ int tps_se(double* l, double* g, double* e, double* p
         const double off = l[A10];   // m[0,1] == m[1,0] (symmetric working matrix)
         eigenvalues_2x2(l[A00], off, off, l[A11], lhi, llo);
         const double en = tail2x2_e(kAlgo, lhi, llo, gamma, delta_prev);
-        e[N - 2] = en;
-        e[N - 1] = en;
+        g[N - 2] = en;
+        g[N - 1] = en;
         double a00 = l[A00], a11 = l[A11];
         if (en > 0.0) {
             a00 = dadd(a00, en);
@@ -1244,16 +1251,15 @@ __device__ __forceinline__ void tps_gmw_column_at(double* w, const double* lrow_
     }
 }
 
-// w: packed triangle (A's lower triangle on entry, L on exit); lrow, cd, d, e, p: N doubles each
+// w: packed triangle (A's lower triangle on entry, L on exit); lrow, cd, d: N doubles each; e_j
+// takes the slot of the running diagonal of position j, which is dead once j has been the pivot
 template <int N>
-__device__ __forceinline__ void tps_gmw(double* w, double* lrow, double* cd, double* d, double* e, double* p)
+__device__ __forceinline__ void tps_gmw(double* w, double* lrow, double* cd, double* d, TpsPerm& p)
 {
     double diag_max = 0.0, off_max = 0.0;   // gmw81.rs:49-58 (the upper triangle mirrors the lower)
     for (int i = 0; i < N; ++i) {
         const int ti = tps_tri(i);
-        e[i] = 0.0;
         d[i] = 0.0;
-        p[i] = (double)i;
         cd[i] = w[ti + i];   // gmw81.rs:66-68
         const double v = fabs(w[ti + i]);
         if (v > diag_max) diag_max = v;
@@ -1278,10 +1284,8 @@ __device__ __forceinline__ void tps_gmw(double* w, double* lrow, double* cd, dou
         }
         if (m != j) {
             tps_swap(w, N, j, m);
-            double t = p[j];
-            p[j] = p[m];
-            p[m] = t;
-            t = cd[j];
+            p.swap(j, m);
+            const double t = cd[j];
             cd[j] = cd[m];
             cd[m] = t;
         }
@@ -1305,7 +1309,7 @@ __device__ __forceinline__ void tps_gmw(double* w, double* lrow, double* cd, dou
             const double cij = w[tps_tri(i) + j];
             cd[i] = dsub(cd[i], ddiv(dmul(cij, cij), dj));
         }
-        e[j] = dsub(dj, cjj);   // gmw81.rs:110
+        cd[j] = dsub(dj, cjj);   // gmw81.rs:110: e_j
     }
     // gmw81.rs:112-125: l . diag(sqrt(d)) with a unit diagonal; the dense product's accumulation
     // from 0.0 turns a -0 into +0
@@ -1327,22 +1331,23 @@ tps_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
     extern __shared__ double sm[];
     constexpr int NN = N * N, T = N * (N + 1) / 2, S = tps_thread_doubles(N, kAlgo);
     double* mine = sm + threadIdx.x * S;
-    double *g = mine + T, *e = g + N, *p = e + N;   // (GMW81: g is d; lrow and cd follow p)
+    double* g = mine + T;   // SE: g / e; GMW81: the running diagonal / e, then lrow and d
     const bool al16 = (((size_t)A | (size_t)L) & 15) == 0, al32 = (((size_t)L) & 31) == 0;
     const long long stride = (long long)gridDim.x * kTpsThreads;
     for (long long b = (long long)blockIdx.x * kTpsThreads + threadIdx.x; b < batch; b += stride) {
         // in: the lower triangle straight from this thread's matrix (see tp_load_lower)
         tp_load_lower<N>(A + (size_t)b * NN, al16, [&](int i, int k, double v) { mine[i * (i + 1) / 2 + k] = v; });
         int kstart = -1;
+        TpsPerm p;
         if constexpr (kAlgo == kGMW81)
-            tps_gmw<N>(mine, p + N, p + 2 * N, g, e, p);
+            tps_gmw<N>(mine, g + N, g, g + 2 * N, p);
         else
-            kstart = tps_se<kAlgo, N>(mine, g, e, p);
+            kstart = tps_se<kAlgo, N>(mine, g, p);
         if (L)   // se90.rs:169-173, se99.rs:189-192, gmw81.rs:119-123
             tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return mine[i * (i + 1) / 2 + k]; });
-        for (int i = 0; i < N; ++i) {   // se90.rs:174-178, se99.rs:194-198
-            const int pi = (int)p[i];
-            if (E) E[(size_t)b * N + pi] = e[i];
+        for (int i = 0; i < N; ++i) {   // se90.rs:174-178, se99.rs:194-198, gmw81.rs:127-131
+            const int pi = p.get(i);
+            if (E) E[(size_t)b * N + pi] = g[i];
             if (P) P[(size_t)b * N + i] = (unsigned long long)pi;
         }
         if (K)
@@ -1376,13 +1381,17 @@ tps_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
         __syncwarp();
         int kstart = -1;
         if (lane < cnt) {
-            double *g = mine + T, *e = g + N, *p = e + N;
+            double* g = mine + T;
+            TpsPerm p;
             if constexpr (kAlgo == kGMW81)
-                tps_gmw<N>(mine, p + N, p + 2 * N, g, e, p);
+                tps_gmw<N>(mine, g + N, g, g + 2 * N, p);
             else
-                kstart = tps_se<kAlgo, N>(mine, g, e, p);
-            for (int i = 0; i < N; ++i)   // e in original order (se90.rs:174-178, se99.rs:194-198): through g
-                g[(int)p[i]] = e[i];
+                kstart = tps_se<kAlgo, N>(mine, g, p);
+            for (int i = 0; i < N; ++i) {   // se90.rs:174-178, se99.rs:194-198, gmw81.rs:127-131
+                const int pi = p.get(i);
+                if (E) E[(size_t)(t0 + lane) * N + pi] = g[i];
+                if (P) P[(size_t)(t0 + lane) * N + i] = (unsigned long long)pi;
+            }
         }
         __syncwarp();
         if (L) {   // L with its strict upper triangle zero (se90.rs:169-173, se99.rs:189-192)
@@ -1390,16 +1399,6 @@ tps_kernel_staged(long long batch, const double* __restrict__ A, double* __restr
             for (int q = lane; q < words; q += kTpsThreads) {
                 const int mat = q / NN, r = q - mat * NN, i = r / N, k = r - i * N;
                 dst[q] = k <= i ? sm[mat * S + i * (i + 1) / 2 + k] : 0.0;
-            }
-        }
-        {
-            const int vwords = cnt * N;
-            for (int q = lane; q < vwords; q += kTpsThreads) {
-                const int mat = q / N, i = q - mat * N;
-                if (E)
-                    E[(size_t)t0 * N + q] = sm[mat * S + T + i];
-                if (P)
-                    P[(size_t)t0 * N + q] = (unsigned long long)sm[mat * S + T + 2 * N + i];
             }
         }
         if (K && lane < cnt)

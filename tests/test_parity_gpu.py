@@ -203,9 +203,10 @@ def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
                     _assert_bit_exact(f"tpm {algo} n={n} {fam} b={b} {mode}", _gpu(torch, algo, a, mode), ref)
     finally:
         m.set_small_kernel_family(prev)
-    # the default dispatch (batches of 512 and more): n <= 8 always; up to n = 12 (GMW81: 9) in FAST and n = 16 in STRICT mode
+    # the default dispatch (batches of 512 and more): n <= 8 always; up to n = 12 (GMW81: 10) in FAST and n = 16 in STRICT mode
     assert m.kernel_class("se99", 8, "fast") == "thread" and m.kernel_class("gmw81", 9, "fast") == "thread"
-    assert m.kernel_class("gmw81", 10, "fast") == "warp_smem" and m.kernel_class("gmw81", 16, "strict") == "thread"
+    assert m.kernel_class("gmw81", 10, "fast") == "thread" and m.kernel_class("gmw81", 11, "fast") == "warp_smem"
+    assert m.kernel_class("gmw81", 16, "strict") == "thread"
     assert m.kernel_class("se99", 12, "fast") == "thread" and m.kernel_class("se99", 13, "fast") == "warp_smem"
     assert m.kernel_class("se90", 16, "strict") == "thread" and m.kernel_class("se90", 17, "strict") == "warp_smem"
 
