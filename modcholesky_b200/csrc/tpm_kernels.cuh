@@ -759,11 +759,27 @@ __device__ __forceinline__ void tp_stg_v4(double* p, double a, double b, double 
 {
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
+__device__ __forceinline__ void tp_ldg_v4(const double* p, double& a, double& b, double& c, double& d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 // put(i, k, value) for every k <= i
 template <int N, typename F>
-__device__ __forceinline__ void tp_load_lower(const double* __restrict__ a, bool al16, F&& put)
+__device__ __forceinline__ void tp_load_lower(const double* __restrict__ a, bool al16, F&& put, bool al32 = false)
 {
-    if (N % 2 == 0 && al16) {
+    if (N % 4 == 0 && al32) {   // one whole sector per thread and instruction
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int k = 0; k <= i; k += 4) {
+                double v0, v1, v2, v3;
+                tp_ldg_v4(a + i * N + k, v0, v1, v2, v3);
+                put(i, k, v0);
+                if (k + 1 <= i) put(i, k + 1, v1);
+                if (k + 2 <= i) put(i, k + 2, v2);
+                if (k + 3 <= i) put(i, k + 3, v3);
+            }
+    } else if (N % 2 == 0 && al16) {
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -815,13 +831,14 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
 {
     constexpr int NN = N * N;
     const bool al16 = (((size_t)A | (size_t)L) & 15) == 0, al32 = (((size_t)L) & 31) == 0;
+    const bool al32a = (((size_t)A) & 31) == 0;
     const long long stride = (long long)gridDim.x * kTpmThreads;
     for (long long b = (long long)blockIdx.x * kTpmThreads + threadIdx.x; b < batch; b += stride) {
         const double* a = A + (size_t)b * NN;
         int kstart = -1;
         if constexpr (kAlgo == kGMW81) {
             TprGmw<N> s;
-            tp_load_lower<N>(a, al16, [&](int i, int k, double v) { s.l(i, k) = v; });
+            tp_load_lower<N>(a, al16, [&](int i, int k, double v) { s.l(i, k) = v; }, al32a);
             tpr_gmw<N>(s);
             if (L)   // gmw81.rs:119-123
                 tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return s.l(i, k); });
@@ -834,7 +851,7 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
                 tpr_solve<N>(s.l, s.p, Bm + (size_t)b * nrhs * N, X + (size_t)b * nrhs * N, nrhs);
         } else {
             TprSe<N> s;
-            tp_load_lower<N>(a, al16, [&](int i, int k, double v) { s.l(i, k) = v; });
+            tp_load_lower<N>(a, al16, [&](int i, int k, double v) { s.l(i, k) = v; }, al32a);
             tpr_se<kAlgo, N>(s);
             kstart = s.kstart;
             if (L)   // se90.rs:169-173, se99.rs:189-192
@@ -1333,10 +1350,11 @@ tps_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
     double* mine = sm + threadIdx.x * S;
     double* g = mine + T;   // SE: g / e; GMW81: the running diagonal / e, then lrow and d
     const bool al16 = (((size_t)A | (size_t)L) & 15) == 0, al32 = (((size_t)L) & 31) == 0;
+    const bool al32a = (((size_t)A) & 31) == 0;
     const long long stride = (long long)gridDim.x * kTpsThreads;
     for (long long b = (long long)blockIdx.x * kTpsThreads + threadIdx.x; b < batch; b += stride) {
         // in: the lower triangle straight from this thread's matrix (see tp_load_lower)
-        tp_load_lower<N>(A + (size_t)b * NN, al16, [&](int i, int k, double v) { mine[i * (i + 1) / 2 + k] = v; });
+        tp_load_lower<N>(A + (size_t)b * NN, al16, [&](int i, int k, double v) { mine[i * (i + 1) / 2 + k] = v; }, al32a);
         int kstart = -1;
         TpsPerm p;
         if constexpr (kAlgo == kGMW81)
