@@ -228,10 +228,11 @@ def other_configs(torch, np, m, dev, peak):
         torch.cuda.empty_cache()
 
     # the reference's fixed-size bench shapes 3x3 / 4x4 (benches/bench.rs:23-44 and the se90 / se99
-    # twins), batched: 2^22 symmetric-uniform matrices through the thread-per-matrix kernels
+    # twins), batched: 2^22 symmetric-uniform matrices through the thread-per-matrix kernels; n = 8
+    # (2^20 matrices) is the upper end of the register-resident class
     small = {}
-    for n in (3, 4):
-        batch = 1 << 22
+    for n in (3, 4, 8):
+        batch = 1 << 22 if n <= 4 else 1 << 20
         a = gen_batch(torch, batch, n, SEED + 17 * n, dev)
         ent = {}
         for algo in ("gmw81", "se90", "se99"):
