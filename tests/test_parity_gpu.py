@@ -201,6 +201,19 @@ def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
                 for mode in ("strict", "fast"):
                     assert m.kernel_class(algo, n, mode) == "thread"
                     _assert_bit_exact(f"tpm {algo} n={n} {fam} b={b} {mode}", _gpu(torch, algo, a, mode), ref)
+            # IEEE specials: zeros (0/0), +-identity, a negative rank-one matrix,
+            # underflowing and overflowing entries, a NaN and an Inf entry -- propagated exactly like
+            # the reference, NaN positions included, in both modes
+            with_nan, with_inf = np.eye(n), np.eye(n)
+            with_nan[n - 1, n - 1] = np.nan
+            with_inf[0, 0] = np.inf
+            specials = np.stack([np.zeros((n, n)), np.eye(n), -np.eye(n), -4.0 * np.ones((n, n)),
+                                 np.full((n, n), 1e-300), np.full((n, n), 1e300) * np.eye(n), with_nan, with_inf])
+            ref = oracle.factor_batched(algo, specials)
+            for mode in ("strict", "fast"):
+                got = _gpu(torch, algo, specials, mode)
+                assert np.array_equal(np.isnan(got[0]), np.isnan(ref.l)), (algo, n, mode, "NaN pattern of L")
+                _assert_bit_exact(f"tpm {algo} n={n} specials {mode}", got, ref)
     finally:
         m.set_small_kernel_family(prev)
     # the default dispatch (batches of 512 and more): n <= 8 always; up to n = 12 (GMW81: 10) in FAST and n = 16 in STRICT mode
