@@ -26,7 +26,9 @@
  *
  * Errors: the reference panics (assert!(is_square), se99.rs:38) or silently
  * propagates NaN/Inf; here every call returns a status (0 = ok, negative = error,
- * text via modchol_last_error()), NaN/Inf are propagated exactly like the reference,
+ * text via modchol_last_error()), NaN/Inf are propagated exactly like the reference (one
+ * exception: GMW81's final dense product l.dot(dout), gmw81.rs:125, spreads a non-finite
+ * entry of L over its whole row through NaN * 0 terms; here it stays in its element),
  * and there is NO CPU fallback: without a usable CUDA device every compute call fails
  * with MODCHOL_ERR_NO_DEVICE.
  *

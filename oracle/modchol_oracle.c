@@ -454,7 +454,12 @@ static int gmw81_factor(size_t n, const double *a, double *l, double *e, uint64_
 
     /* gmw81.rs:112-125: unit diagonal, zero upper, l = l . diag(sqrt(d)).  The dense
      * `dot` has exactly one non-zero term per output element; the accumulation of the
-     * remaining exact zeros only normalises a -0 result to +0 (0.0 + x). */
+     * remaining exact zeros only normalises a -0 result to +0 (0.0 + x).
+     * KNOWN DIVERGENCE for NON-FINITE factors: in the reference's dense product a NaN or
+     * Inf entry l_ik meets the zeros of dout's other columns (NaN * 0, Inf * 0) and turns
+     * the WHOLE row i of L into NaN, and an infinite sqrt(d_q) meets the zeros of the upper
+     * triangle (0 * Inf); this restatement (and the CUDA kernels) propagate non-finite
+     * values only through the one meaningful term.  Finite factorisations are unaffected. */
     for (size_t i = 0; i < n; ++i) {
         for (size_t q = 0; q < n; ++q) {
             double v;
