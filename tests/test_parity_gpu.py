@@ -184,7 +184,7 @@ def test_both_small_kernel_families_are_bit_exact(oracle, torch_cuda, family):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16])
-def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
+def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, monkeypatch, n):
     """One thread per matrix (tpm_kernels.cuh): tiles of 128 matrices -- batches below one tile,
     of several tiles and with a ragged last tile; both modes run the reference's arithmetic, so
     FAST is bit-exact too; every family including exact ties and the bench-style Q D Q^T inputs."""
@@ -216,6 +216,18 @@ def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, n):
                 _assert_bit_exact(f"tpm {algo} n={n} specials {mode}", got, ref)
     finally:
         m.set_small_kernel_family(prev)
+    # the run-time-n variant of the class (MODCHOL_TPR=0: full matrix per thread in shared memory)
+    if n <= 8:
+        monkeypatch.setenv("MODCHOL_TPR", "0")
+        prev = m.set_small_kernel_family("tpm")
+        try:
+            for algo in ALGOS:
+                a = matgen.make("wishart", 9900 + n, 200, n)
+                _assert_bit_exact(f"tpm(run-time n) {algo} n={n}", _gpu(torch, algo, a, "strict"),
+                                  oracle.factor_batched(algo, a))
+        finally:
+            m.set_small_kernel_family(prev)
+            monkeypatch.delenv("MODCHOL_TPR")
     # the default dispatch (batches of 512 and more): n <= 8 always; up to n = 12 (GMW81: 10) in FAST and n = 16 in STRICT mode
     assert m.kernel_class("se99", 8, "fast") == "thread" and m.kernel_class("gmw81", 9, "fast") == "thread"
     assert m.kernel_class("gmw81", 10, "fast") == "thread" and m.kernel_class("gmw81", 11, "fast") == "warp_smem"
