@@ -465,6 +465,8 @@ template <int kAlgo, int N, int J>
 __device__ __forceinline__ void tpr_se_step(TprSe<N>& s)
 {
     TprTri<N>& l = s.l;
+    bool elim = false;   // ONE elimination site per column: in a warp whose matrices are in different
+                         // phases the two pivot paths run one after the other, the elimination once
     if (s.ph1) {   // phase 1: se90.rs:61-96, se99.rs:61-109
         if (kAlgo == kSE99) {   // se99.rs:62-73
             double dmax = -INFINITY, dmin = INFINITY;
@@ -504,7 +506,7 @@ __device__ __forceinline__ void tpr_se_step(TprSe<N>& s)
                 s.ph1 = false;
         }
         if (s.ph1) {
-            tpr_eliminate<N, J>(l);
+            elim = true;
         } else {
             s.kstart = J;   // phase 2 starts at this column
             if (kAlgo == kSE99 && J == N - 1) {   // se99.rs:115-119
@@ -561,9 +563,11 @@ __device__ __forceinline__ void tpr_se_step(TprSe<N>& s)
                 for (int i = J + 1; i < N; ++i)
                     s.g[i] = dadd(s.g[i], dmul(fabs(l(i, J)), t));
             }
-            tpr_eliminate<N, J>(l);
+            elim = true;
         }
     }
+    if (elim)
+        tpr_eliminate<N, J>(l);
 }
 template <int kAlgo, int N, int J>
 __device__ __forceinline__ void tpr_se_steps(TprSe<N>& s)
