@@ -150,7 +150,7 @@ const char *modchol_kernel_class(int algo, int mode, int32_t n);
 
 /* Tuning knob: which small-n kernel family serves n <= 32 -- 0 = automatic (one thread per
  * matrix, "thread", for n <= 8 and up to n = 12 (GMW81: 10) in FAST and n = 16 in STRICT mode,
- * batches of 512 matrices and more;
+ * batches of 512 (n <= 8) / 4096 (n > 8) matrices and more;
  * the shared-memory-resident "warp_smem" family above), 1 = register-resident "warp32", 2 =
  * shared-memory-resident ("warp_smem" always serves 32 < n <= 64), 3 = "thread" wherever it
  * exists (n <= 16).

@@ -239,7 +239,10 @@ int small_kernel_pref()
 
 int cta_ld(int n) { return (n & 1) ? n : n + 1; }
 
-constexpr long long kThreadMinBatch = 512;   // below: the warp kernels (factor_device)
+// below this batch the warp kernels serve the call (factor_device): one thread per matrix needs a
+// batch to fill the machine.  Measured for 8 < n <= 16 (STRICT, gpurun_out/exp_batch.txt): 2 048
+// matrices 77 against 56 us (n = 10), 8 192 matrices 78 against 110 us.
+inline long long thread_min_batch(int n) { return n <= kTpmMaxNHost ? 512 : 4096; }
 
 // largest n served by the thread-per-matrix kernels by default (MODCHOL_TPM_MAX / MODCHOL_TPS_MAX,
 // tuning knobs read per call; 0 switches them off)
@@ -343,7 +346,7 @@ int factor_device(int dev, int algo, int mode, long long batch, int n, const dou
     KernelClass cls = classify(algo, mode, n, c.smem_optin);
     // one thread per matrix needs a batch to fill the machine: a handful of matrices (the trait
     // call on one Array2) is served faster by a warp per matrix (12 x 12: 21 against 27 us)
-    if (cls == kClsThread && batch < kThreadMinBatch && small_kernel_pref() != 3)
+    if (cls == kClsThread && batch < thread_min_batch(n) && small_kernel_pref() != 3)
         cls = kClsWarpSmem;
     if (cls == kClsWarp) {
         cudaError_t ce = launch_warp_kernel(algo, mode, n, batch, a, l, e, p, k, c.sms, st);
@@ -553,7 +556,7 @@ int factor_solve_device(int dev, int algo, int mode, long long batch, int n, int
     // kernel followed by the solve kernel is ahead of the fused warp kernels: SE99 n=16 STRICT 213
     // against 196 M systems/s)
     KernelClass cls = classify(algo, mode, n, c.smem_optin);
-    if (cls == kClsThread && batch < kThreadMinBatch && small_kernel_pref() != 3)
+    if (cls == kClsThread && batch < thread_min_batch(n) && small_kernel_pref() != 3)
         cls = kClsWarpSmem;
     if (cls == kClsThread && n <= kTpmMaxNHost) {
         cudaError_t ce = launch_tpm_solve_kernel(algo, n, batch, a, l, e, p, k, b, x, nrhs, c.sms, st);

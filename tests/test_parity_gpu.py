@@ -228,7 +228,7 @@ def test_thread_per_matrix_kernels_are_bit_exact(oracle, torch_cuda, monkeypatch
         finally:
             m.set_small_kernel_family(prev)
             monkeypatch.delenv("MODCHOL_TPR")
-    # the default dispatch (batches of 512 and more): n <= 8 always; up to n = 12 (GMW81: 10) in FAST and n = 16 in STRICT mode
+    # the default dispatch (batches of 512 and more, 4096 for n > 8): n <= 8 always; up to n = 12 (GMW81: 10) in FAST and n = 16 in STRICT mode
     assert m.kernel_class("se99", 8, "fast") == "thread" and m.kernel_class("gmw81", 9, "fast") == "thread"
     assert m.kernel_class("gmw81", 10, "fast") == "thread" and m.kernel_class("gmw81", 11, "fast") == "warp_smem"
     assert m.kernel_class("gmw81", 16, "strict") == "thread"
@@ -458,8 +458,8 @@ def test_eight_byte_aligned_buffers(oracle, torch_cuda):
     # (the last five cases reach the thread-per-matrix kernels, whose direct accesses are 128-bit
     # loads and 256-bit stores when the bases allow: off = 2 is 16- but not 32-byte aligned)
     for algo, n, b, off in (("se99", 32, 300, 1), ("se90", 16, 300, 1), ("gmw81", 24, 200, 1), ("se99", 64, 50, 1),
-                            ("se99", 8, 700, 1), ("se99", 8, 700, 2), ("gmw81", 2, 600, 1), ("se90", 12, 600, 2),
-                            ("gmw81", 16, 600, 1)):
+                            ("se99", 8, 700, 1), ("se99", 8, 700, 2), ("gmw81", 2, 600, 1), ("se90", 12, 4200, 2),
+                            ("gmw81", 16, 4200, 1)):
         a = matgen.make("uniform", 70 + n, b, n)
         ref = oracle.factor_batched(algo, a)
         for mode in ("strict", "fast"):
