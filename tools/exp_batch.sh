@@ -1,5 +1,6 @@
-for b in 2048 8192 16384 32768 65536 131072; do
-for t in 16 0; do
-  echo "=== batch $b MODCHOL_TPS_MAX=$t"
-  MODCHOL_SMALL_KERNEL= MODCHOL_TPS_MAX=$t python tools/quick_bench.py --cases se99:10:$b,se99:12:$b,se99:16:$b --modes strict --families uniform --reps 9 | awk '{print $1,$2,$3,$6,$7,$8,$9,$10}'
+# thread-per-matrix (default) against the warp kernels (MODCHOL_TPM_MAX=0 / MODCHOL_TPS_MAX=0) at small batches
+for b in 512 2048 8192; do
+for t in 8 0; do
+  echo "=== batch $b MODCHOL_TPM_MAX=$t"
+  MODCHOL_TPM_MAX=$t python tools/quick_bench.py --cases se99:4:$b,se99:6:$b,se99:8:$b --modes strict,fast --families uniform --reps 9 | awk '{print $1,$2,$3,$5,$6,$7,$8,$9,$10}'
 done; done
