@@ -25,14 +25,15 @@ static cudaError_t launch_tpm_algo(int n, long long batch, const double* a, doub
 }
 
 // compile-time n, everything in registers (n <= kTprMaxN).  Direct per-thread global accesses
-// where one thread moves at least a sector's worth per instruction pair (n = 2, 8), the tile
+// where one thread moves whole sectors per instruction (n = 2, 4, 8: rows of 32-byte multiples, e
+// and p as 256-bit stores too), the tile
 // staged through shared memory otherwise (measured: profiles/r02_thread_per_matrix.txt).
 template <int kAlgo, int N, bool kSolve>
 static cudaError_t launch_tpr_n(long long batch, const double* a, double* l, double* e,
                                 unsigned long long* p, int* k, int sms, cudaStream_t st,
                                 const double* rhs, double* x, int nrhs)
 {
-    constexpr bool kDirect = N == 2 || N == 8;
+    constexpr bool kDirect = N == 2 || N == 4 || N == 8;
     long long blocks = (batch + kTpmThreads - 1) / kTpmThreads;
     if constexpr (kDirect) {
         auto kern = tpr_kernel<kAlgo, N, kSolve>;

@@ -827,6 +827,45 @@ __device__ __forceinline__ void tp_store_full(double* __restrict__ dst, bool al3
     }
 }
 
+// e (un-permuted: gmw81.rs:127-131, se90.rs:174-178, se99.rs:194-198) and p of one matrix.  With
+// N a multiple of 4 and aligned bases both vectors leave as 256-bit stores -- e is brought into
+// original order in registers first (a select chain over p) -- instead of 2 N scattered 8-byte
+// stores, 32 sectors per warp instruction each.
+template <int N>
+__device__ __forceinline__ void tp_store_e_p(double* E, unsigned long long* P, long long b,
+                                             const double (&e)[N], const int (&p)[N])
+{
+    const bool vec = N % 4 == 0 && ((((size_t)E) | ((size_t)P)) & 31) == 0;
+    if (vec) {
+        if (E) {
+            double eo[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                eo[k] = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    eo[k] = p[i] == k ? e[i] : eo[k];
+            }
+#pragma unroll
+            for (int k = 0; k < N; k += 4)
+                tp_stg_v4(E + (size_t)b * N + k, eo[k], eo[k + 1], eo[k + 2], eo[k + 3]);
+        }
+        if (P) {
+#pragma unroll
+            for (int k = 0; k < N; k += 4)
+                tp_stg_v4(reinterpret_cast<double*>(P + (size_t)b * N + k), __longlong_as_double((long long)p[k]),
+                          __longlong_as_double((long long)p[k + 1]), __longlong_as_double((long long)p[k + 2]),
+                          __longlong_as_double((long long)p[k + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (E) E[(size_t)b * N + p[i]] = e[i];
+            if (P) P[(size_t)b * N + i] = (unsigned long long)p[i];
+        }
+    }
+}
+
 template <int kAlgo, int N, bool kSolve = false>
 __global__ void __launch_bounds__(kTpmThreads)
 tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L,
@@ -846,11 +885,7 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
             tpr_gmw<N>(s);
             if (L)   // gmw81.rs:119-123
                 tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return s.l(i, k); });
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                if (E) E[(size_t)b * N + s.p[i]] = s.e[i];   // gmw81.rs:127-131
-                if (P) P[(size_t)b * N + i] = (unsigned long long)s.p[i];
-            }
+            tp_store_e_p<N>(E, P, b, s.e, s.p);
             if constexpr (kSolve)
                 tpr_solve<N>(s.l, s.p, Bm + (size_t)b * nrhs * N, X + (size_t)b * nrhs * N, nrhs);
         } else {
@@ -860,11 +895,7 @@ tpr_kernel(long long batch, const double* __restrict__ A, double* __restrict__ L
             kstart = s.kstart;
             if (L)   // se90.rs:169-173, se99.rs:189-192
                 tp_store_full<N>(L + (size_t)b * NN, al32, al16, [&](int i, int k) { return s.l(i, k); });
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                if (E) E[(size_t)b * N + s.p[i]] = s.e[i];   // se90.rs:174-178, se99.rs:194-198
-                if (P) P[(size_t)b * N + i] = (unsigned long long)s.p[i];
-            }
+            tp_store_e_p<N>(E, P, b, s.e, s.p);
             if constexpr (kSolve)
                 tpr_solve<N>(s.l, s.p, Bm + (size_t)b * nrhs * N, X + (size_t)b * nrhs * N, nrhs);
         }
